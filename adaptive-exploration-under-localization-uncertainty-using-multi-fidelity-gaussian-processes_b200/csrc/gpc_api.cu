@@ -1,0 +1,650 @@
+// gpc_api.cu -- C ABI of libgpcore.so (see include/gpcore.h).  Host-side orchestration only:
+// every numerical step is one of the CUDA kernels in gpc_factor.cuh / gpc_predict.cuh /
+// gpc_ig.cuh; there is no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gpcore.h"
+#include "gpc_factor.cuh"
+#include "gpc_ig.cuh"
+#include "gpc_predict.cuh"
+
+#define GPC_VERSION 100
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  double* d() const { return static_cast<double*>(p); }
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct gpc_handle_s {
+  int kind = 0, F = 1, device = 0;
+  cudaStream_t stream = nullptr;
+  GpcHyp hyp;
+  bool have_hyp = false, have_data = false, factored = false;
+  long N = 0, n_pad = 0;
+  int nb = 0;
+  double logdet = 0.0, nlml = 0.0;
+  long m_chunk = 16384;
+  long launches = 0;
+  std::string err;
+  // model state
+  DevBuf Xt, y, extra, L, X, T, alpha, vec, partial, scal, status;
+  bool have_extra = false;
+  // prediction workspaces
+  DevBuf Xs4, Kx, meanpart, sumsq, gradpart, mean, var, Vt, cov, grads, ediag;
+  // information-gain workspaces
+  DevBuf gX4, gVt, gS, gSinv, gT, Bt, Zt, cand_off, cand_I, cand_aux;
+  // hot-kernel timing
+  bool hot_timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double hot_ms = 0.0;
+  long hot_launches = 0;
+};
+
+namespace {
+
+int fail(gpc_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(h, GPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+#define CKL()                                                                                           \
+  do {                                                                                                  \
+    ++h->launches;                                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                               \
+    if (e__ != cudaSuccess) return fail(h, GPC_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
+
+int set_gemm_attrs(gpc_handle h) {
+  const int sm = gpcg::SMEM_BYTES;
+  CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_syrk_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_linv_level, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_vt<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_vt<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_vt<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_cross_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
+  return GPC_OK;
+}
+
+// Blocked right-looking Cholesky of the n_pad x n_pad matrix A (in place, lower) followed by the
+// triangular inverse X = L^-1 (recursive doubling, scratch T).  d_status: device int, 0 = PD.
+int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int* d_status) {
+  const int nb = (int)(n_pad / 128);
+  cudaStream_t s = h->stream;
+  CK(cudaMemsetAsync(d_status, 0, sizeof(int), s));
+  for (int p = 0; p < nb; ++p) {
+    k_potrf_diag<<<1, 512, GPC_POTRF_SMEM, s>>>(A, X, n_pad, p, d_status);
+    CKL();
+    const int m = nb - p - 1;
+    if (m > 0) {
+      k_trsm_panel<<<m, gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(A, X, n_pad, p);
+      CKL();
+      k_syrk_panel<<<dim3(m, m), gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(A, n_pad, p);
+      CKL();
+    }
+  }
+  for (int sb = 1; sb < nb; sb *= 2) {
+    const int nodes = (nb + 2 * sb - 1) / (2 * sb);
+    for (int phase = 0; phase < 2; ++phase) {
+      k_linv_level<<<dim3(sb, sb, nodes), gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, sb, phase);
+      CKL();
+    }
+  }
+  return GPC_OK;
+}
+
+// out = M^T x (+ bias) via two-stage partial sums.
+int trmv_t(gpc_handle h, const double* M, const double* x, const double* bias, double bias_scale, double sign,
+           double* out) {
+  const int nb = h->nb;
+  k_trmv_t_partial<<<dim3(nb, nb), 128, 0, h->stream>>>(M, h->n_pad, x, h->partial.d(), h->n_pad);
+  CKL();
+  k_colsum_partial<<<(unsigned)((h->n_pad + 255) / 256), 256, 0, h->stream>>>(h->partial.d(), nb, h->n_pad, bias,
+                                                                            bias_scale, sign, out);
+  CKL();
+  return GPC_OK;
+}
+
+// alpha = L^-T L^-1 y with the explicit inverse as the solver and one step of iterative
+// refinement against L itself per triangular system (restores a backward-stable residual).
+int solve_alpha(gpc_handle h) {
+  const long np = h->n_pad;
+  cudaStream_t s = h->stream;
+  double* z = h->vec.d();
+  double* r = z + np;
+  double* dz = z + 2 * np;
+  double* al = h->alpha.d();
+  const double *L = h->L.d(), *X = h->X.d(), *y = h->y.d();
+  const unsigned gr = (unsigned)((np + 7) / 8), ga = (unsigned)((np + 255) / 256);
+  k_trmv_n<<<gr, 256, 0, s>>>(X, np, np, y, nullptr, 0.0, 1.0, z);  CKL();
+  k_trmv_n<<<gr, 256, 0, s>>>(L, np, np, z, y, 1.0, -1.0, r);        CKL();
+  k_trmv_n<<<gr, 256, 0, s>>>(X, np, np, r, nullptr, 0.0, 1.0, dz);  CKL();
+  k_axpy<<<ga, 256, 0, s>>>(z, dz, np);                              CKL();
+  int rc;
+  if ((rc = trmv_t(h, X, z, nullptr, 0.0, 1.0, al))) return rc;
+  if ((rc = trmv_t(h, L, al, z, 1.0, -1.0, r))) return rc;
+  if ((rc = trmv_t(h, X, r, nullptr, 0.0, 1.0, dz))) return rc;
+  k_axpy<<<ga, 256, 0, s>>>(al, dz, np);                             CKL();
+  return GPC_OK;
+}
+
+int require_factor(gpc_handle h) {
+  if (!h) return GPC_ERR_ARG;
+  if (!h->factored) return fail(h, GPC_ERR_STATE, "model not factored: call gpc_factor first");
+  return GPC_OK;
+}
+
+int ensure_pred_ws(gpc_handle h, long m_pad, bool need_vt, bool need_grad) {
+  const long np = h->n_pad;
+  const int nchunks = (int)((np + KS_COLS - 1) / KS_COLS);
+  CK(h->Kx.ensure((size_t)m_pad * np * 8));
+  CK(h->meanpart.ensure((size_t)nchunks * m_pad * 8));
+  CK(h->sumsq.ensure((size_t)h->nb * m_pad * 8));
+  if (need_vt) CK(h->Vt.ensure((size_t)m_pad * np * 8));
+  if (need_grad) CK(h->gradpart.ensure((size_t)nchunks * 3 * m_pad * 8));
+  return GPC_OK;
+}
+
+template <bool WITH_GRAD, bool STORE_K>
+int launch_kstar(gpc_handle h, const double* dXs4, long M, long m_pad) {
+  const long np = h->n_pad;
+  const int nchunks = (int)((np + KS_COLS - 1) / KS_COLS);
+  k_kstar<WITH_GRAD, STORE_K><<<dim3((unsigned)(m_pad / KS_ROWS), nchunks), 256, 0, h->stream>>>(
+      h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, dXs4, M, m_pad, h->Kx.d(), h->meanpart.d(),
+      WITH_GRAD ? h->gradpart.d() : nullptr);
+  CKL();
+  return GPC_OK;
+}
+
+template <bool STORE_V, bool SUMSQ>
+int launch_vt(gpc_handle h, long m_pad) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->hot_timing) {
+    if (h->ev_used + 2 > h->ev.size()) {
+      for (int i = 0; i < 64; ++i) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->ev.push_back(e);
+      }
+    }
+    e0 = h->ev[h->ev_used++];
+    e1 = h->ev[h->ev_used++];
+    CK(cudaEventRecord(e0, h->stream));
+  }
+  k_vt<STORE_V, SUMSQ><<<dim3((unsigned)(m_pad / 128), h->nb), gpcg::NTHREADS, gpcg::SMEM_BYTES, h->stream>>>(
+      h->Kx.d(), h->X.d(), h->n_pad, h->nb, m_pad, h->Vt.d(), h->sumsq.d());
+  CKL();
+  if (h->hot_timing) CK(cudaEventRecord(e1, h->stream));
+  return GPC_OK;
+}
+
+// One chunk of the posterior (device pointers; M <= m_chunk).
+int predict_chunk(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags) {
+  const long m_pad = round_up(M, 128);
+  int rc;
+  if ((rc = ensure_pred_ws(h, m_pad, false, false))) return rc;
+  const bool want_var = dvar && !(flags & GPC_MEAN_ONLY);
+  if (want_var) {
+    if ((rc = launch_kstar<false, true>(h, dXs4, M, m_pad))) return rc;
+    if ((rc = launch_vt<false, true>(h, m_pad))) return rc;
+  } else {
+    if ((rc = launch_kstar<false, false>(h, dXs4, M, m_pad))) return rc;
+  }
+  const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
+  k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(h->hyp, dXs4, M, m_pad, h->meanpart.d(),
+                                                                       nchunks, h->sumsq.d(), h->nb, dmean,
+                                                                       want_var ? dvar : nullptr, flags);
+  CKL();
+  return GPC_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int gpc_version(void) { return GPC_VERSION; }
+
+const char* gpc_last_error(gpc_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gpc_create(int kind, int F, int device, gpc_handle* out) {
+  gpc_handle h = nullptr;
+  if (!out) return fail(nullptr, GPC_ERR_ARG, "out == NULL");
+  *out = nullptr;
+  if (kind < GPC_SF_RBF || kind > GPC_NIGP) return fail(nullptr, GPC_ERR_ARG, "unknown model kind");
+  const bool mf = (kind == GPC_MF_AR1_RBF || kind == GPC_MF_AR1_MAT32);
+  if (F < 1 || F > GPC_MAXF || (!mf && F != 1)) return fail(nullptr, GPC_ERR_SHAPE, "bad fidelity count");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, GPC_ERR_CUDA,
+                std::string("no CUDA device (gpcore has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, GPC_ERR_ARG, "bad device ordinal");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, GPC_ERR_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10)
+    return fail(nullptr, GPC_ERR_CUDA, "gpcore is built for sm_100a (Blackwell B200) only");
+  h = new gpc_handle_s();
+  h->kind = kind;
+  h->F = F;
+  h->device = device;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    std::string m = cudaGetErrorString(e);
+    delete h;
+    return fail(nullptr, GPC_ERR_CUDA, m);
+  }
+  int rc = set_gemm_attrs(h);
+  if (rc) {
+    g_create_error = h->err;
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return GPC_OK;
+}
+
+int gpc_destroy(gpc_handle h) {
+  if (!h) return GPC_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
+                    &h->status, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
+                    &h->cov, &h->grads, &h->ediag, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
+                    &h->cand_off, &h->cand_I, &h->cand_aux};
+  for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return GPC_OK;
+}
+
+int gpc_set_hypers(gpc_handle h, const double* p, int n, double jitter) {
+  if (!h || !p) return GPC_ERR_ARG;
+  GpcHyp g;
+  memset(&g, 0, sizeof(g));
+  g.F = h->F;
+  g.jitter = jitter;
+  const int F = h->F;
+  auto bad = [&](const char* m) { return fail(h, GPC_ERR_SHAPE, m); };
+  if (h->kind == GPC_SF_RBF || h->kind == GPC_SF_MAT32) {
+    if (n != 5) return bad("single-fidelity hypers: expected [variance, lx, ly, lz, noise_var]");
+    g.base = (h->kind == GPC_SF_MAT32);
+    g.var[0] = p[0];
+    for (int d = 0; d < 3; ++d) g.inv_l[0][d] = 1.0 / p[1 + d];
+    g.noise[0] = p[4];
+    g.coef[0][0] = 1.0;
+  } else if (h->kind == GPC_NIGP) {
+    if (n != 5) return bad("NIGP hypers: expected [lx, ly, lz, sigma_f, sigma_y]");
+    g.base = 0;
+    for (int d = 0; d < 3; ++d) g.inv_l[0][d] = 1.0 / sqrt(1.0 / (1.0 / (p[d] * p[d])));  // inv_l=True round trip
+    g.var[0] = p[3];           // NIGP.py:18 passes sigma_f as the kernel variance
+    g.noise[0] = p[4] * p[4];  // sigma_y is a standard deviation (NIGP.py:41)
+    g.coef[0][0] = 1.0;
+  } else {
+    const int n1 = 4 * F + (F - 1) + 1, nF = 4 * F + (F - 1) + F;
+    if (n != n1 && n != nF) return bad("multi-fidelity hypers: expected 4F + (F-1) + (1|F) values");
+    g.base = (h->kind == GPC_MF_AR1_MAT32);
+    for (int m = 0; m < F; ++m) {
+      g.var[m] = p[4 * m];
+      for (int d = 0; d < 3; ++d) g.inv_l[m][d] = 1.0 / p[4 * m + 1 + d];
+    }
+    const double* rho = p + 4 * F;
+    for (int i = 0; i < F; ++i)
+      for (int m = 0; m <= i; ++m) {
+        double c = 1.0;
+        for (int l = m; l < i; ++l) c *= rho[l];
+        g.coef[i][m] = c;
+      }
+    const double* nz = p + 4 * F + F - 1;
+    for (int i = 0; i < F; ++i) g.noise[i] = (n == n1) ? nz[0] : nz[i];
+  }
+  for (int i = 0; i < F; ++i) {
+    double v = 0.0;
+    for (int m = 0; m <= i; ++m) v += g.coef[i][m] * g.coef[i][m] * g.var[m];
+    g.kdiag[i] = v;
+  }
+  for (int m = 0; m < F; ++m) {
+    if (!(g.var[m] >= 0.0) || !std::isfinite(g.var[m])) return bad("kernel variance must be finite and >= 0");
+    for (int d = 0; d < 3; ++d)
+      if (!std::isfinite(g.inv_l[m][d])) return bad("lengthscales must be non-zero and finite");
+  }
+  h->hyp = g;
+  h->have_hyp = true;
+  h->factored = false;
+  return GPC_OK;
+}
+
+int gpc_set_data(gpc_handle h, const double* X4, const double* y, const double* extra, long N) {
+  if (!h || !X4 || !y) return GPC_ERR_ARG;
+  if (N < 1) return fail(h, GPC_ERR_SHAPE, "N must be >= 1");
+  CK(cudaSetDevice(h->device));
+  const long np = round_up(N, 128);
+  std::vector<double> soa((size_t)4 * np, 0.0), yp((size_t)np, 0.0);
+  for (long i = 0; i < N; ++i) {
+    for (int c = 0; c < 4; ++c) soa[(size_t)c * np + i] = X4[i * 4 + c];
+    yp[i] = y[i];
+  }
+  CK(h->Xt.ensure((size_t)4 * np * 8));
+  CK(h->y.ensure((size_t)np * 8));
+  CK(h->alpha.ensure((size_t)np * 8));
+  CK(h->vec.ensure((size_t)3 * np * 8));
+  CK(h->scal.ensure(64));
+  CK(h->status.ensure(64));
+  CK(cudaMemcpyAsync(h->Xt.p, soa.data(), (size_t)4 * np * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->y.p, yp.data(), (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
+  h->have_extra = extra != nullptr;
+  if (extra) {
+    std::vector<double> ep((size_t)np, 0.0);
+    memcpy(ep.data(), extra, (size_t)N * 8);
+    CK(h->extra.ensure((size_t)np * 8));
+    CK(cudaMemcpyAsync(h->extra.p, ep.data(), (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->N = N;
+  h->n_pad = np;
+  h->nb = (int)(np / 128);
+  h->have_data = true;
+  h->factored = false;
+  return GPC_OK;
+}
+
+int gpc_factor(gpc_handle h, double* nlml, double* logdet) {
+  if (!h) return GPC_ERR_ARG;
+  if (!h->have_hyp || !h->have_data) return fail(h, GPC_ERR_STATE, "set hypers and data before gpc_factor");
+  CK(cudaSetDevice(h->device));
+  const long np = h->n_pad;
+  const int nb = h->nb;
+  CK(h->L.ensure((size_t)np * np * 8));
+  CK(h->X.ensure((size_t)np * np * 8));
+  CK(h->T.ensure((size_t)np * np * 8));
+  CK(h->partial.ensure((size_t)nb * np * 8));
+  h->factored = false;
+  k_assemble_train<<<dim3(nb, nb), 256, 0, h->stream>>>(h->hyp, h->Xt.d(), h->have_extra ? h->extra.d() : nullptr,
+                                                        h->L.d(), h->N, np);
+  CKL();
+  int rc = factor_matrix(h, h->L.d(), h->X.d(), h->T.d(), np, static_cast<int*>(h->status.p));
+  if (rc) return rc;
+  int st = 0;
+  CK(cudaMemcpyAsync(&st, h->status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (st != 0) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "covariance not positive definite (pivot block %d)", st - 1);
+    return fail(h, GPC_ERR_NOT_PD, buf);
+  }
+  if ((rc = solve_alpha(h))) return rc;
+  k_logdet_fit<<<1, 1024, 0, h->stream>>>(h->L.d(), np, h->N, h->y.d(), h->alpha.d(), h->scal.d());
+  CKL();
+  double sc[2];
+  CK(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (!std::isfinite(sc[0]) || !std::isfinite(sc[1]))
+    return fail(h, GPC_ERR_NOT_PD, "non-finite factor (covariance not positive definite)");
+  h->logdet = sc[0];
+  h->nlml = 0.5 * sc[1] + 0.5 * sc[0] + 0.5 * (double)h->N * log(2.0 * M_PI);
+  h->factored = true;
+  if (nlml) *nlml = h->nlml;
+  if (logdet) *logdet = h->logdet;
+  return GPC_OK;
+}
+
+long gpc_padded_n(gpc_handle h) { return h ? h->n_pad : 0; }
+
+int gpc_get_alpha(gpc_handle h, double* alpha) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(alpha, h->alpha.p, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return GPC_OK;
+}
+
+static int get_lower(gpc_handle h, const double* dsrc, double* out) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy2DAsync(out, (size_t)h->N * 8, dsrc, (size_t)h->n_pad * 8, (size_t)h->N * 8, (size_t)h->N,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (long i = 0; i < h->N; ++i)
+    for (long j = i + 1; j < h->N; ++j) out[i * h->N + j] = 0.0;
+  return GPC_OK;
+}
+
+int gpc_get_chol(gpc_handle h, double* L) {
+  int rc = require_factor(h);
+  return rc ? rc : get_lower(h, h->L.d(), L);
+}
+
+int gpc_get_linv(gpc_handle h, double* Linv) {
+  int rc = require_factor(h);
+  return rc ? rc : get_lower(h, h->X.d(), Linv);
+}
+
+int gpc_factor_state_dev(gpc_handle h, double** L, double** Linv, double** alpha, long* n_pad) {
+  if (!h) return GPC_ERR_ARG;
+  if (!h->have_hyp || !h->have_data) return fail(h, GPC_ERR_STATE, "set hypers and data first");
+  CK(cudaSetDevice(h->device));
+  const long np = h->n_pad;
+  CK(h->L.ensure((size_t)np * np * 8));
+  CK(h->X.ensure((size_t)np * np * 8));
+  CK(h->partial.ensure((size_t)h->nb * np * 8));
+  if (L) *L = h->L.d();
+  if (Linv) *Linv = h->X.d();
+  if (alpha) *alpha = h->alpha.d();
+  if (n_pad) *n_pad = np;
+  return GPC_OK;
+}
+
+int gpc_adopt_factor(gpc_handle h, double logdet) {
+  if (!h) return GPC_ERR_ARG;
+  if (!h->have_hyp || !h->have_data || !h->L.p || !h->X.p)
+    return fail(h, GPC_ERR_STATE, "gpc_adopt_factor needs hypers, data and gpc_factor_state_dev buffers");
+  h->logdet = logdet;
+  h->factored = true;
+  return GPC_OK;
+}
+
+int gpc_kernel_matrix(gpc_handle h, const double* Xa4, long na, const double* Xb4, long nb_, double* K) {
+  if (!h || !Xa4 || !K) return GPC_ERR_ARG;
+  if (!h->have_hyp) return fail(h, GPC_ERR_STATE, "set hypers first");
+  if (!Xb4) { Xb4 = Xa4; nb_ = na; }
+  if (na < 1 || nb_ < 1) return fail(h, GPC_ERR_SHAPE, "empty input");
+  CK(cudaSetDevice(h->device));
+  DevBuf a, b, k;
+  cudaError_t e;
+  int rc = GPC_OK;
+  if ((e = a.ensure((size_t)na * 32)) || (e = b.ensure((size_t)nb_ * 32)) || (e = k.ensure((size_t)na * nb_ * 8))) {
+    rc = fail(h, GPC_ERR_CUDA, cudaGetErrorString(e));
+  } else {
+    cudaMemcpyAsync(a.p, Xa4, (size_t)na * 32, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(b.p, Xb4, (size_t)nb_ * 32, cudaMemcpyHostToDevice, h->stream);
+    k_kernel_matrix<<<dim3((unsigned)((nb_ + 31) / 32), (unsigned)((na + 7) / 8)), 256, 0, h->stream>>>(
+        h->hyp, a.d(), na, b.d(), nb_, k.d());
+    ++h->launches;
+    cudaMemcpyAsync(K, k.p, (size_t)na * nb_ * 8, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(h, GPC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  a.release(); b.release(); k.release();
+  return rc;
+}
+
+int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  if (M < 0 || !dXs4) return fail(h, GPC_ERR_SHAPE, "bad test set");
+  CK(cudaSetDevice(h->device));
+  for (long o = 0; o < M; o += h->m_chunk) {
+    const long m = (M - o) < h->m_chunk ? (M - o) : h->m_chunk;
+    if ((rc = predict_chunk(h, dXs4 + o * 4, m, dmean ? dmean + o : nullptr, dvar ? dvar + o : nullptr, flags)))
+      return rc;
+  }
+  return GPC_OK;
+}
+
+int gpc_predict(gpc_handle h, const double* Xs4, long M, double* mean, double* var, unsigned flags) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  if (M < 0 || (M > 0 && !Xs4)) return fail(h, GPC_ERR_SHAPE, "bad test set");
+  if (M == 0) return GPC_OK;
+  CK(cudaSetDevice(h->device));
+  const long mc = h->m_chunk;
+  CK(h->Xs4.ensure((size_t)mc * 32));
+  CK(h->mean.ensure((size_t)mc * 8));
+  CK(h->var.ensure((size_t)mc * 8));
+  const bool want_var = var && !(flags & GPC_MEAN_ONLY);
+  for (long o = 0; o < M; o += mc) {
+    const long m = (M - o) < mc ? (M - o) : mc;
+    CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + o * 4, (size_t)m * 32, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = predict_chunk(h, h->Xs4.d(), m, mean ? h->mean.d() : nullptr, want_var ? h->var.d() : nullptr, flags)))
+      return rc;
+    if (mean) CK(cudaMemcpyAsync(mean + o, h->mean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (want_var) CK(cudaMemcpyAsync(var + o, h->var.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return GPC_OK;
+}
+
+int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, double* cov, const double* extra_diag,
+                    unsigned flags) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  if (M < 1 || !Xs4 || !cov) return fail(h, GPC_ERR_SHAPE, "bad test set");
+  if (M > 32768) return fail(h, GPC_ERR_SHAPE, "full covariance limited to M <= 32768");
+  CK(cudaSetDevice(h->device));
+  const long m_pad = round_up(M, 128);
+  if ((rc = ensure_pred_ws(h, m_pad, true, false))) return rc;
+  CK(h->Xs4.ensure((size_t)m_pad * 32));
+  CK(h->cov.ensure((size_t)M * M * 8));
+  CK(h->mean.ensure((size_t)m_pad * 8));
+  CK(cudaMemcpyAsync(h->Xs4.p, Xs4, (size_t)M * 32, cudaMemcpyHostToDevice, h->stream));
+  if (extra_diag) {
+    CK(h->ediag.ensure((size_t)M * 8));
+    CK(cudaMemcpyAsync(h->ediag.p, extra_diag, (size_t)M * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  if ((rc = launch_kstar<false, true>(h, h->Xs4.d(), M, m_pad))) return rc;
+  if ((rc = launch_vt<true, false>(h, m_pad))) return rc;
+  const int mt = (int)(m_pad / 128);
+  k_cov<<<dim3(mt, mt), gpcg::NTHREADS, gpcg::SMEM_BYTES, h->stream>>>(
+      h->hyp, h->Vt.d(), h->n_pad, h->Xs4.d(), M, extra_diag ? h->ediag.d() : nullptr, h->cov.d(), flags);
+  CKL();
+  if (mean) {
+    const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
+    k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(
+        h->hyp, h->Xs4.d(), M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, h->mean.d(), nullptr, flags);
+    CKL();
+    CK(cudaMemcpyAsync(mean, h->mean.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaMemcpyAsync(cov, h->cov.p, (size_t)M * M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return GPC_OK;
+}
+
+int gpc_mean_grad(gpc_handle h, const double* Xs4, long M, double* mean, double* grads) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  if (M < 1 || !Xs4 || !grads) return fail(h, GPC_ERR_SHAPE, "bad test set");
+  if (h->F != 1) return fail(h, GPC_ERR_ARG, "mean gradients are defined for single-fidelity kernels");
+  CK(cudaSetDevice(h->device));
+  const long mc = h->m_chunk;
+  CK(h->Xs4.ensure((size_t)mc * 32));
+  CK(h->mean.ensure((size_t)mc * 8));
+  CK(h->grads.ensure((size_t)mc * 24));
+  const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
+  for (long o = 0; o < M; o += mc) {
+    const long m = (M - o) < mc ? (M - o) : mc;
+    const long m_pad = round_up(m, 128);
+    if ((rc = ensure_pred_ws(h, m_pad, false, true))) return rc;
+    CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + o * 4, (size_t)m * 32, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_kstar<true, false>(h, h->Xs4.d(), m, m_pad))) return rc;
+    k_finalize_pred<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(
+        h->hyp, h->Xs4.d(), m, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, h->mean.d(), nullptr, 0u);
+    CKL();
+    k_finalize_grad<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(h->gradpart.d(), nchunks, m, m_pad,
+                                                                         h->grads.d());
+    CKL();
+    if (mean) CK(cudaMemcpyAsync(mean + o, h->mean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(grads + o * 3, h->grads.p, (size_t)m * 24, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return GPC_OK;
+}
+
+void* gpc_stream(gpc_handle h) { return h ? (void*)h->stream : nullptr; }
+long gpc_launch_count(gpc_handle h) { return h ? h->launches : 0; }
+
+int gpc_set_chunk(gpc_handle h, long m_chunk) {
+  if (!h) return GPC_ERR_ARG;
+  if (m_chunk < 128 || m_chunk % 128) return fail(h, GPC_ERR_SHAPE, "chunk must be a positive multiple of 128");
+  h->m_chunk = m_chunk;
+  return GPC_OK;
+}
+
+int gpc_enable_hot_timing(gpc_handle h, int on) {
+  if (!h) return GPC_ERR_ARG;
+  h->hot_timing = on != 0;
+  return GPC_OK;
+}
+
+int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, int reset) {
+  if (!h) return GPC_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    h->hot_ms += ms;
+    ++h->hot_launches;
+  }
+  h->ev_used = 0;
+  if (ms_total) *ms_total = h->hot_ms;
+  if (launches) *launches = h->hot_launches;
+  if (reset) { h->hot_ms = 0.0; h->hot_launches = 0; }
+  return GPC_OK;
+}
+
+#include "gpc_ig_api.inc"
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// gpc_factor.cuh -- covariance assembly, blocked right-looking FP64 Cholesky, triangular
+// inverse by recursive doubling, and the alpha / log-det solves.
+//
+// Storage: all N x N operands are row-major with leading dimension n_pad (N rounded up to 128);
+// only tiles on or below the block diagonal are ever touched.  Rows/columns >= N are an identity
+// block, so the padded factor is [[L, 0], [0, I]] and contributes nothing to log-det or solves.
+#pragma once
+#include "gpc_gemm.cuh"
+
+// ------------------------------------------------------------------------------------------
+// K + diag(noise) for the training set.  Xt is SoA: x[n_pad], y[n_pad], z[n_pad], f[n_pad].
+// replaces: NIGP.py:41-42,150-151,285-287; GPy exact_gaussian_inference (K + (noise+1e-8) I).
+// grid (nb, nb) over lower tiles, 256 threads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble_train(const __grid_constant__ GpcHyp h,
+                                                        const double* __restrict__ Xt,
+                                                        const double* __restrict__ extra, double* __restrict__ K,
+                                                        long N, long n_pad) {
+  const int jb = blockIdx.x, ib = blockIdx.y;
+  if (jb > ib) return;
+  const double *xs = Xt, *ys = Xt + n_pad, *zs = Xt + 2 * n_pad, *fs = Xt + 3 * n_pad;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const long j = (long)jb * 128 + tx + 32 * c;
+    const double bx = xs[j], by = ys[j], bz = zs[j], bf = fs[j];
+#pragma unroll 4
+    for (int r = 0; r < 16; ++r) {
+      const long i = (long)ib * 128 + ty + 8 * r;
+      double v;
+      if (i >= N || j >= N) {
+        v = (i == j) ? 1.0 : 0.0;
+      } else {
+        v = gpc_kval(h, xs[i], ys[i], zs[i], fs[i], bx, by, bz, bf);
+        if (i == j) v += h.noise[gpc_fid(h, bf)] + h.jitter + (extra ? extra[i] : 0.0);
+      }
+      K[i * n_pad + j] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagonal block p: L_pp = chol(A_pp) and X_pp = L_pp^-1, one CTA, register-resident.
+// Thread (j = tid/4, q = tid%4) owns column j, rows i = 4s + q (s = 0..31).
+// Right-looking elimination with the pivot column broadcast through shared memory (one
+// __syncthreads per column); the inverse is a column-parallel forward substitution that only
+// needs warp shuffles.  status receives p + 1 for the first non-positive pivot.
+// replaces: scipy cho_factor (NIGP.py:43,154,288) / LAPACK dpotrf inside GPy pdinv.
+// ------------------------------------------------------------------------------------------
+#define GPC_PD_LD 129
+constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 256 + 128) * 8;
+
+__global__ void __launch_bounds__(512, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
+                                                       int p, int* __restrict__ status) {
+  extern __shared__ double sm[];
+  double* Ls = sm;
+  double* col = sm + 128 * GPC_PD_LD;
+  double* invd = col + 256;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = tid >> 2, q = tid & 3;
+  double* Ap = A + (long)p * 128 * ld + (long)p * 128;
+  double* Xp = X + (long)p * 128 * ld + (long)p * 128;
+
+  for (int e = tid; e < 128 * 128; e += 512) {
+    const int r = e >> 7, c = e & 127;
+    Ls[r * GPC_PD_LD + c] = Ap[(long)r * ld + c];
+  }
+  __syncthreads();
+  double a[32];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    const int i = 4 * s + q;
+    a[s] = (i >= j) ? Ls[i * GPC_PD_LD + j] : 0.0;
+  }
+  __syncthreads();
+
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 128; ++k) {
+    double* ck = col + (k & 1) * 128;
+    if (j == k) {
+      double d = __shfl_sync(0xFu << (lane & ~3), a[k >> 2], (lane & ~3) + (k & 3));
+      if (!(d > 0.0)) { bad = true; d = 1.0; }
+      const double dd = sqrt(d), inv = 1.0 / dd;
+#pragma unroll
+      for (int s = (k >> 2); s < 32; ++s) {
+        const int i = 4 * s + q;
+        if (i > k) { a[s] *= inv; ck[i] = a[s]; }
+        else if (i == k) { a[s] = dd; ck[i] = dd; }
+      }
+    }
+    __syncthreads();
+    if (j > k) {
+      const double ljk = ck[j];
+#pragma unroll
+      for (int s = (k >> 2); s < 32; ++s) {
+        const int i = 4 * s + q;
+        if (i >= j) a[s] = fma(-ck[i], ljk, a[s]);
+      }
+    }
+  }
+  if (bad) atomicCAS(status, 0, p + 1);
+
+  // L tile (zeros above the diagonal) -> shared -> global
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    const int i = 4 * s + q;
+    Ls[i * GPC_PD_LD + j] = (i >= j) ? a[s] : 0.0;
+    if (i == j) invd[j] = 1.0 / a[s];
+  }
+  __syncthreads();
+  for (int e = tid; e < 128 * 128; e += 512) {
+    const int r = e >> 7, c = e & 127;
+    Ap[(long)r * ld + c] = Ls[r * GPC_PD_LD + c];
+  }
+
+  // X = L^-1: thread group j solves L x = e_j
+  double x[32];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) x[s] = (4 * s + q == j) ? 1.0 : 0.0;
+  const int kmin = warp * 8;  // x_k == 0 for k < j; every column of this warp has j >= 8 * warp
+#pragma unroll
+  for (int k = 0; k < 128; ++k) {
+    if (k >= kmin) {
+      const double xk = __shfl_sync(0xffffffffu, x[k >> 2], (lane & ~3) + (k & 3)) * invd[k];
+      if (q == (k & 3)) x[k >> 2] = xk;
+#pragma unroll
+      for (int s = (k >> 2); s < 32; ++s) {
+        const int i = 4 * s + q;
+        if (i > k) x[s] = fma(-Ls[i * GPC_PD_LD + k], xk, x[s]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    const int i = 4 * s + q;
+    Ls[i * GPC_PD_LD + j] = (i >= j) ? x[s] : 0.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < 128 * 128; e += 512) {
+    const int r = e >> 7, c = e & 127;
+    Xp[(long)r * ld + c] = Ls[r * GPC_PD_LD + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Panel solve: L_ip = A_ip * X_pp^T  for i > p (TRSM expressed as a DMMA contraction with the
+// inverted diagonal block).  grid = nb - p - 1.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_trsm_panel(double* __restrict__ A,
+                                                                  const double* __restrict__ X, long ld, int p) {
+  extern __shared__ double sm[];
+  const int i = p + 1 + blockIdx.x;
+  double acc[4][4][2];
+  gpcg::zero_acc(acc);
+  double* Aip = A + (long)i * 128 * ld + (long)p * 128;
+  const double* Xpp = X + (long)p * 128 * ld + (long)p * 128;
+  gpcg::mainloop<false>(Aip, ld, Xpp, ld, 0, 128, acc, sm);
+  gpcg::store_tile(Aip, ld, acc, 1.0, 0.0);
+}
+
+// Trailing update: A_ij -= L_ip L_jp^T for p < j <= i.  grid (m, m), m = nb - p - 1.
+__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_syrk_panel(double* __restrict__ A, long ld, int p) {
+  extern __shared__ double sm[];
+  const int j = p + 1 + blockIdx.x, i = p + 1 + blockIdx.y;
+  if (j > i) return;
+  double acc[4][4][2];
+  gpcg::zero_acc(acc);
+  gpcg::mainloop<false>(A + (long)i * 128 * ld + (long)p * 128, ld, A + (long)j * 128 * ld + (long)p * 128, ld, 0,
+                        128, acc, sm);
+  gpcg::store_tile(A + (long)i * 128 * ld + (long)j * 128, ld, acc, -1.0, 1.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// Triangular inverse by recursive doubling.  At level `sb` (half-size in tiles) node q covers
+// tiles [a0, a0 + 2 sb) with split mid = a0 + sb:
+//   phase 0:  T[B, A] = L[B, A] * X[A, A]          (k over A-range, >= column tile)
+//   phase 1:  X[B, A] = - X[B, B] * T[B, A]        (k over B-range, <= row tile)
+// grid (sb, sb, nodes); tiles past the matrix end exit.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_linv_level(const double* __restrict__ L,
+                                                                  double* __restrict__ X,
+                                                                  double* __restrict__ T, long ld, int nb, int sb,
+                                                                  int phase) {
+  extern __shared__ double sm[];
+  const int a0 = blockIdx.z * 2 * sb, mid = a0 + sb;
+  const int aj = a0 + blockIdx.x, bi = mid + blockIdx.y;
+  if (bi >= nb) return;
+  double acc[4][4][2];
+  gpcg::zero_acc(acc);
+  if (phase == 0) {
+    gpcg::mainloop<true>(L + (long)bi * 128 * ld, ld, X + (long)aj * 128, ld, aj * 128, mid * 128, acc, sm);
+    gpcg::store_tile(T + (long)bi * 128 * ld + (long)aj * 128, ld, acc, 1.0, 0.0);
+  } else {
+    gpcg::mainloop<true>(X + (long)bi * 128 * ld, ld, T + (long)aj * 128, ld, mid * 128, (bi + 1) * 128, acc, sm);
+    gpcg::store_tile(X + (long)bi * 128 * ld + (long)aj * 128, ld, acc, -1.0, 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Lower-triangular mat-vec helpers (bandwidth bound, used once per factorisation):
+//   mode 0:  out = bias_scale * bias + sign * M x        (M lower, row access; warp per row)
+//   mode 1:  partial[rb][j] = sum_{i in row block rb, i >= j} M(i, j) x(i)   (M^T x, two-stage)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trmv_n(const double* __restrict__ M, long ld, long n,
+                                                const double* __restrict__ x, const double* __restrict__ bias,
+                                                double bias_scale, double sign, double* __restrict__ out) {
+  const long i = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const double* row = M + i * ld;
+  double s = 0.0;
+  for (long j = lane; j <= i; j += 32) s = fma(row[j], x[j], s);
+  s = warp_sum(s);
+  if (lane == 0) out[i] = (bias ? bias_scale * bias[i] : 0.0) + sign * s;
+}
+
+__global__ void __launch_bounds__(128) k_trmv_t_partial(const double* __restrict__ M, long ld,
+                                                        const double* __restrict__ x,
+                                                        double* __restrict__ partial, long n_pad) {
+  const int cb = blockIdx.x, rb = blockIdx.y;
+  const long j = (long)cb * 128 + threadIdx.x;
+  double s = 0.0;
+  if (rb >= cb) {
+    const long i0 = (long)rb * 128;
+#pragma unroll 8
+    for (int r = 0; r < 128; ++r) {
+      const long i = i0 + r;
+      const double m = M[i * ld + j];
+      s = fma((i >= j) ? m : 0.0, x[i], s);
+    }
+  }
+  partial[(long)rb * n_pad + j] = s;
+}
+
+__global__ void __launch_bounds__(256) k_colsum_partial(const double* __restrict__ partial, int nrb, long n_pad,
+                                                        const double* __restrict__ bias, double bias_scale,
+                                                        double sign, double* __restrict__ out) {
+  const long j = (long)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n_pad) return;
+  double s = 0.0;
+  for (int rb = 0; rb < nrb; ++rb) s += partial[(long)rb * n_pad + j];
+  out[j] = (bias ? bias_scale * bias[j] : 0.0) + sign * s;
+}
+
+__global__ void __launch_bounds__(256) k_axpy(double* __restrict__ y, const double* __restrict__ x, long n) {
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+// scal[0] = logdet = 2 sum log L_ii ; scal[1] = y' alpha.  One CTA.
+// replaces NIGP.py:159-161 (warp-shuffle reductions of the diagonal and the data-fit dot).
+__global__ void __launch_bounds__(1024) k_logdet_fit(const double* __restrict__ L, long ld, long N,
+                                                     const double* __restrict__ y,
+                                                     const double* __restrict__ alpha, double* __restrict__ scal) {
+  __shared__ double s0[32], s1[32];
+  double a = 0.0, b = 0.0;
+  for (long i = threadIdx.x; i < N; i += 1024) {
+    a += log(L[i * ld + i]);
+    b = fma(y[i], alpha[i], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = a; s1[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = warp_sum(s0[threadIdx.x]);
+    b = warp_sum(s1[threadIdx.x]);
+    if (threadIdx.x == 0) { scal[0] = 2.0 * a; scal[1] = b; }
+  }
+}

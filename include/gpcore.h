@@ -1,0 +1,137 @@
+/*
+ * gpcore.h -- C ABI of libgpcore.so, the B200 (sm_100a) dense Gaussian-process inference core.
+ *
+ * The reference (colem404/Adaptive-Exploration-...-Multi-fidelity-Gaussian-Processes) is pure
+ * Python and has no FFI layer; its boundary is the duck-typed model protocol
+ * (fit / predict / predict_covariance / set_XY / set_data / CalcCost).  Each entry point below
+ * names the reference call it replaces (paths relative to the reference checkout).  The Python
+ * host shim (package `gpcore`) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns an int status (GPC_OK == 0); gpc_last_error() gives the message;
+ *   - all matrices are C-contiguous float64; "X4" rows are (x, y, z, fidelity index) -- unused
+ *     spatial columns must be 0, single-fidelity models ignore the 4th column;
+ *   - pointers are HOST pointers unless the function name ends in _dev (then they are device
+ *     pointers on the handle's device and the call is asynchronous on gpc_stream());
+ *   - the caller owns every buffer it passes; the handle owns all device state;
+ *   - a handle is not thread-safe: one handle per host thread (the reference only ever calls
+ *     its GP from the planner thread, PhysicalExperimentCode/GraceExplorationExperiments_MFGP.py:767);
+ *   - a non positive-definite covariance is a recoverable status (GPC_ERR_NOT_PD), mirroring the
+ *     LinAlgError the reference catches at NIGP.py:156 and ...MFGP.py:392.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns GPC_ERR_CUDA.
+ */
+#ifndef GPCORE_H
+#define GPCORE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpc_handle_s* gpc_handle;
+
+enum gpc_status {
+  GPC_OK = 0,
+  GPC_ERR_NOT_PD = 1, /* Cholesky met a non-positive pivot */
+  GPC_ERR_SHAPE = 2,  /* bad N / M / k / F / parameter-vector length */
+  GPC_ERR_CUDA = 3,   /* CUDA runtime error (message in gpc_last_error) */
+  GPC_ERR_STATE = 4,  /* call order: data/hypers/factor missing */
+  GPC_ERR_ARG = 5
+};
+
+enum gpc_kind {
+  GPC_SF_RBF = 0,       /* GPy GPRegression + RBF(ARD)       GPTrainers.py:80-84 */
+  GPC_SF_MAT32 = 1,     /* GPy GPRegression + Matern32(ARD)  PhysicalExperimentCode/...SFGP.py:610 */
+  GPC_MF_AR1_RBF = 2,   /* emukit LinearMultiFidelityKernel over RBF    GPTrainers.py:62-66 */
+  GPC_MF_AR1_MAT32 = 3, /* ... over Matern32   PhysicalExperimentCode/...MFGP.py:656 */
+  GPC_NIGP = 4          /* NIGP.py SE-ARD with heteroscedastic diagonal; sigma_f is the kernel variance */
+};
+
+/* gpc_predict flags */
+#define GPC_INCLUDE_NOISE 1u /* add the likelihood variance (GPy predict default)                */
+#define GPC_CLIP_DIAG 2u     /* clip the latent marginal variance at 1e-15 (GPy)                  */
+#define GPC_CLIP_COV 4u      /* clip the whole covariance element-wise at 1e-10 (emukit wrapper)  */
+#define GPC_NIGP_FLOOR 8u    /* NIGP.py:327-333: var = max(var + 1e-12, 1e-12); cov += 1e-12 I    */
+#define GPC_MEAN_ONLY 16u    /* skip the variance (var may be NULL)                               */
+
+/* gpc_ig_seq flags */
+#define GPC_IG_FIRST_PREADDED 1u /* GraceRIGV3.py:454-455: point 0 is appended before it is predicted */
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* F = number of fidelities (1 for SF / NIGP, <= 4).  device = CUDA ordinal. */
+int gpc_create(int kind, int F, int device, gpc_handle* out);
+int gpc_destroy(gpc_handle h);
+const char* gpc_last_error(gpc_handle h); /* h may be NULL: last creation error */
+int gpc_version(void);
+
+/* ---- model state -------------------------------------------------------------------------- */
+/* Flat hyper-parameter vector in the reference's own `param_array` order:
+ *   SF   (n=5):  variance, lx, ly, lz, noise_var                    (...SFGP.py:620)
+ *   MF   (n=4F + F-1 + (1|F)): per fidelity (variance, lx, ly, lz), rho_1..rho_{F-1},
+ *         noise | noise_0..noise_{F-1}                               (...MFGP.py:670)
+ *   NIGP (n=5):  lx, ly, lz, sigma_f (kernel variance!), sigma_y (std) (NIGP.py:137-141)
+ * jitter is added to the training diagonal: 1e-8 for the GPy models (exact_gaussian_inference),
+ * 1e-8 inside NIGP's NLML (NIGP.py:152-154), 0 in NIGP.predict (NIGP.py:287). */
+int gpc_set_hypers(gpc_handle h, const double* flat, int n, double jitter);
+
+/* Training set: X4 is N x 4, y is N, extra_noise_diag (N, may be NULL) is the per-point variance
+ * added to the diagonal (NIGP's v_i, NIGP.py:147,286).  Replaces set_XY / set_data. */
+int gpc_set_data(gpc_handle h, const double* X4, const double* y, const double* extra_noise_diag, long N);
+
+/* Assemble K + noise, Cholesky-factor it, solve for alpha, build L^-1.  Outputs may be NULL.
+ * nlml = 0.5 y'alpha + 0.5 logdet + 0.5 N log(2 pi)  (NIGP.py:159-161; GPy -log_marginal). */
+int gpc_factor(gpc_handle h, double* nlml, double* logdet);
+
+/* Copies of the factor state for tests and for the multi-GPU broadcast. */
+int gpc_get_alpha(gpc_handle h, double* alpha /* N */);
+int gpc_get_chol(gpc_handle h, double* L /* N x N, lower, row-major */);
+int gpc_get_linv(gpc_handle h, double* Linv /* N x N, lower, row-major */);
+long gpc_padded_n(gpc_handle h);
+/* Device pointers of the replicated factor state (padded) so that rank 0 can
+ * NCCL-broadcast it; after receiving, the other ranks call gpc_adopt_factor(). */
+int gpc_factor_state_dev(gpc_handle h, double** L, double** Linv, double** alpha, long* n_pad);
+int gpc_adopt_factor(gpc_handle h, double logdet);
+
+/* ---- kernel matrix (NIGP.py:11-20 SE_ARD_kernel; gpy_model.kern.K, GraceRIGV3.py:515) ------ */
+/* K is na x nb; Xb4 == NULL means K(Xa, Xa).  No noise is added. */
+int gpc_kernel_matrix(gpc_handle h, const double* Xa4, long na, const double* Xb4, long nb, double* K);
+
+/* ---- posterior (NIGP.py:269-333; GPy predict; emukit wrapper predict) ----------------------- */
+int gpc_predict(gpc_handle h, const double* Xs4, long M, double* mean, double* var, unsigned flags);
+int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags);
+/* Full M x M posterior covariance (GPy predict(full_cov=1), emukit predict_covariance,
+ * NIGP.predict(return_cov=1)); mean may be NULL.  extra_diag (M, may be NULL) is added to the
+ * diagonal (NIGP's test-input noise term, NIGP.py:321-324). */
+int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, double* cov,
+                    const double* extra_diag, unsigned flags);
+/* Posterior mean and its input gradients, NIGP.py:55-64 / :307-311:
+ * grads[n][d] = sum_j alpha_j k(x_n, x_j) (-(x_nd - x_jd) / l_d^2);  grads is M x 3. */
+int gpc_mean_grad(gpc_handle h, const double* Xs4, long M, double* mean, double* grads);
+
+/* ---- information gain (GraceRIGV3.py:443-562, PhysicalExperimentCode/GraceRIGV3.py:571-678) - */
+/* Candidates are ragged: candidate c owns rows offsets[c] .. offsets[c+1]-1 of Xc4 (<= 64 rows).
+ * Sequential IG:  I_c = sum_i log(1 + s_i / sig_n), s_i = noise-inclusive predictive variance of
+ * point i (queried at fidelity pred_fid when pred_fid >= 0, else at its own fidelity) given the
+ * data and the candidate's earlier points appended with zero targets.
+ * best (may be NULL) receives argmax_c I_c. */
+int gpc_ig_seq(gpc_handle h, const double* Xc4, const long* offsets, long C, double sig_n,
+               int pred_fid, unsigned flags, double* I_out, long* best);
+/* Log-det IG on a fixed grid:  I_c = 0.5 (logdet S_prior(grid) - logdet S_post(grid | data u X_c)),
+ * S = noise-inclusive predictive covariance (calcPathInfoSFBatch / calculatePathInfoEmuBatch).
+ * logdet_prior (may be NULL) receives logdet S_prior. */
+int gpc_ig_logdet(gpc_handle h, const double* grid4, long G, const double* Xc4, const long* offsets,
+                  long C, double* I_out, double* logdet_prior, long* best);
+
+/* ---- measurement hooks ---------------------------------------------------------------------- */
+void* gpc_stream(gpc_handle h);                 /* cudaStream_t all kernels are launched on     */
+long gpc_launch_count(gpc_handle h);            /* kernels launched by this handle so far        */
+int gpc_set_chunk(gpc_handle h, long m_chunk);  /* test points per launch batch (default 16384)  */
+/* Device time of the dominant kernel (the L^-1 K* DMMA contraction) accumulated with CUDA events
+ * on gpc_stream() since the last reset, and the number of its launches. */
+int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, int reset);
+int gpc_enable_hot_timing(gpc_handle h, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPCORE_H */

@@ -57,12 +57,13 @@ struct gpc_handle_s {
   // prediction workspaces
   DevBuf Xs4, Kx, meanpart, sumsq, gradpart, mean, var, Vt, cov, grads, ediag;
   // information-gain workspaces
-  DevBuf gX4, gVt, gS, gSinv, gT, Bt, Zt, cand_off, cand_I, cand_aux;
+  DevBuf gX4, gVt, gS, gSinv, gT, Bt, Zt, cand_off, cand_I, cand_aux, cand_rows, cand_mask, gram, gramZ;
   // hot-kernel timing
   bool hot_timing = false;
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   double hot_ms = 0.0;
+  double hot_flops = 0.0;
   long hot_launches = 0;
 };
 
@@ -100,6 +101,9 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_vt<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_cross_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_gram_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_ig_seq_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
+  CK(cudaFuncSetAttribute(k_ig_logdet_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
   return GPC_OK;
 }
@@ -194,8 +198,10 @@ int launch_kstar(gpc_handle h, const double* dXs4, long M, long m_pad) {
   return GPC_OK;
 }
 
+// V^T = A X^T for an [m_pad][ld] operand A and an explicit lower-triangular inverse X (ld x ld):
+// the dominant DMMA contraction, timed with CUDA events on the handle's stream when enabled.
 template <bool STORE_V, bool SUMSQ>
-int launch_vt(gpc_handle h, long m_pad) {
+int launch_vt_on(gpc_handle h, const double* A, const double* X, long ld, long m_pad, double* Vt, double* sumsq) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->hot_timing) {
     if (h->ev_used + 2 > h->ev.size()) {
@@ -209,29 +215,41 @@ int launch_vt(gpc_handle h, long m_pad) {
     e1 = h->ev[h->ev_used++];
     CK(cudaEventRecord(e0, h->stream));
   }
-  k_vt<STORE_V, SUMSQ><<<dim3((unsigned)(m_pad / 128), h->nb), gpcg::NTHREADS, gpcg::SMEM_BYTES, h->stream>>>(
-      h->Kx.d(), h->X.d(), h->n_pad, h->nb, m_pad, h->Vt.d(), h->sumsq.d());
+  k_vt<STORE_V, SUMSQ><<<dim3((unsigned)(m_pad / 128), (unsigned)(ld / 128)), gpcg::NTHREADS, gpcg::SMEM_BYTES,
+                         h->stream>>>(A, X, ld, (int)(ld / 128), m_pad, Vt, sumsq);
   CKL();
-  if (h->hot_timing) CK(cudaEventRecord(e1, h->stream));
+  if (h->hot_timing) {
+    CK(cudaEventRecord(e1, h->stream));
+    h->hot_flops += (double)m_pad * (double)ld * (double)(ld + 128);  // 2 * m_pad * sum_ib (ib+1) 128 * 128
+  }
   return GPC_OK;
 }
 
-// One chunk of the posterior (device pointers; M <= m_chunk).
-int predict_chunk(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags) {
+template <bool STORE_V, bool SUMSQ>
+int launch_vt(gpc_handle h, long m_pad) {
+  return launch_vt_on<STORE_V, SUMSQ>(h, h->Kx.d(), h->X.d(), h->n_pad, m_pad, h->Vt.d(), h->sumsq.d());
+}
+
+// One chunk of the posterior (device pointers; M <= m_chunk).  d_sx != NULL adds the NIGP
+// test-input-noise term (needs the mean gradients, so the gradient variant of k_kstar runs).
+int predict_chunk(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags,
+                  const double* d_sx = nullptr, long sx_rows = 0) {
   const long m_pad = round_up(M, 128);
   int rc;
-  if ((rc = ensure_pred_ws(h, m_pad, false, false))) return rc;
+  if ((rc = ensure_pred_ws(h, m_pad, false, d_sx != nullptr))) return rc;
   const bool want_var = dvar && !(flags & GPC_MEAN_ONLY);
   if (want_var) {
-    if ((rc = launch_kstar<false, true>(h, dXs4, M, m_pad))) return rc;
+    if (d_sx) rc = launch_kstar<true, true>(h, dXs4, M, m_pad);
+    else rc = launch_kstar<false, true>(h, dXs4, M, m_pad);
+    if (rc) return rc;
     if ((rc = launch_vt<false, true>(h, m_pad))) return rc;
   } else {
     if ((rc = launch_kstar<false, false>(h, dXs4, M, m_pad))) return rc;
   }
   const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
-  k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(h->hyp, dXs4, M, m_pad, h->meanpart.d(),
-                                                                       nchunks, h->sumsq.d(), h->nb, dmean,
-                                                                       want_var ? dvar : nullptr, flags);
+  k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(
+      h->hyp, dXs4, M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, h->gradpart.d(),
+      want_var ? d_sx : nullptr, sx_rows, dmean, want_var ? dvar : nullptr, flags);
   CKL();
   return GPC_OK;
 }
@@ -292,7 +310,7 @@ int gpc_destroy(gpc_handle h) {
   DevBuf* bufs[] = {&h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
                     &h->status, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
                     &h->cov, &h->grads, &h->ediag, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
-                    &h->cand_off, &h->cand_I, &h->cand_aux};
+                    &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -524,27 +542,47 @@ int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, dou
   return GPC_OK;
 }
 
-int gpc_predict(gpc_handle h, const double* Xs4, long M, double* mean, double* var, unsigned flags) {
+static int predict_host(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows, double* mean,
+                        double* var, unsigned flags) {
   int rc = require_factor(h);
   if (rc) return rc;
   if (M < 0 || (M > 0 && !Xs4)) return fail(h, GPC_ERR_SHAPE, "bad test set");
+  if (sx && sx_rows != 1 && sx_rows != M) return fail(h, GPC_ERR_SHAPE, "input-noise array must be (1 x 3) or (M x 3)");
+  if (sx && h->F != 1) return fail(h, GPC_ERR_ARG, "input-noise correction is defined for single-fidelity kernels");
   if (M == 0) return GPC_OK;
   CK(cudaSetDevice(h->device));
   const long mc = h->m_chunk;
   CK(h->Xs4.ensure((size_t)mc * 32));
   CK(h->mean.ensure((size_t)mc * 8));
   CK(h->var.ensure((size_t)mc * 8));
+  if (sx) {
+    CK(h->ediag.ensure((size_t)(sx_rows == 1 ? 1 : mc) * 24));
+    if (sx_rows == 1) CK(cudaMemcpyAsync(h->ediag.p, sx, 24, cudaMemcpyHostToDevice, h->stream));
+  }
   const bool want_var = var && !(flags & GPC_MEAN_ONLY);
   for (long o = 0; o < M; o += mc) {
     const long m = (M - o) < mc ? (M - o) : mc;
     CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + o * 4, (size_t)m * 32, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = predict_chunk(h, h->Xs4.d(), m, mean ? h->mean.d() : nullptr, want_var ? h->var.d() : nullptr, flags)))
+    if (sx && sx_rows != 1)
+      CK(cudaMemcpyAsync(h->ediag.p, sx + o * 3, (size_t)m * 24, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = predict_chunk(h, h->Xs4.d(), m, mean ? h->mean.d() : nullptr, want_var ? h->var.d() : nullptr, flags,
+                            sx ? h->ediag.d() : nullptr, sx_rows)))
       return rc;
     if (mean) CK(cudaMemcpyAsync(mean + o, h->mean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
     if (want_var) CK(cudaMemcpyAsync(var + o, h->var.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   return GPC_OK;
+}
+
+int gpc_predict(gpc_handle h, const double* Xs4, long M, double* mean, double* var, unsigned flags) {
+  return predict_host(h, Xs4, M, nullptr, 0, mean, var, flags);
+}
+
+int gpc_predict_noisy(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows, double* mean,
+                      double* var, unsigned flags) {
+  if (!sx) return fail(h, GPC_ERR_ARG, "sx == NULL");
+  return predict_host(h, Xs4, M, sx, sx_rows, mean, var, flags);
 }
 
 int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, double* cov, const double* extra_diag,
@@ -568,12 +606,13 @@ int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, doubl
   if ((rc = launch_vt<true, false>(h, m_pad))) return rc;
   const int mt = (int)(m_pad / 128);
   k_cov<<<dim3(mt, mt), gpcg::NTHREADS, gpcg::SMEM_BYTES, h->stream>>>(
-      h->hyp, h->Vt.d(), h->n_pad, h->Xs4.d(), M, extra_diag ? h->ediag.d() : nullptr, h->cov.d(), flags);
+      h->hyp, h->Vt.d(), h->n_pad, h->Xs4.d(), M, extra_diag ? h->ediag.d() : nullptr, h->cov.d(), M, 0, flags);
   CKL();
   if (mean) {
     const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
     k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(
-        h->hyp, h->Xs4.d(), M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, h->mean.d(), nullptr, flags);
+        h->hyp, h->Xs4.d(), M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, nullptr, nullptr, 0, h->mean.d(),
+        nullptr, flags);
     CKL();
     CK(cudaMemcpyAsync(mean, h->mean.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
   }
@@ -600,7 +639,8 @@ int gpc_mean_grad(gpc_handle h, const double* Xs4, long M, double* mean, double*
     CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + o * 4, (size_t)m * 32, cudaMemcpyHostToDevice, h->stream));
     if ((rc = launch_kstar<true, false>(h, h->Xs4.d(), m, m_pad))) return rc;
     k_finalize_pred<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(
-        h->hyp, h->Xs4.d(), m, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, h->mean.d(), nullptr, 0u);
+        h->hyp, h->Xs4.d(), m, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, nullptr, nullptr, 0, h->mean.d(),
+        nullptr, 0u);
     CKL();
     k_finalize_grad<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(h->gradpart.d(), nchunks, m, m_pad,
                                                                          h->grads.d());
@@ -628,7 +668,7 @@ int gpc_enable_hot_timing(gpc_handle h, int on) {
   return GPC_OK;
 }
 
-int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, int reset) {
+int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, double* flops, int reset) {
   if (!h) return GPC_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -641,10 +681,11 @@ int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, int rese
   h->ev_used = 0;
   if (ms_total) *ms_total = h->hot_ms;
   if (launches) *launches = h->hot_launches;
-  if (reset) { h->hot_ms = 0.0; h->hot_launches = 0; }
+  if (flops) *flops = h->hot_flops;
+  if (reset) { h->hot_ms = 0.0; h->hot_launches = 0; h->hot_flops = 0.0; }
   return GPC_OK;
 }
 
-#include "gpc_ig_api.inc"
-
 }  // extern "C"
+
+#include "gpc_ig_api.inc"

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(1024) k_logdet_fit(const double* __restrict__ 
   double a = 0.0, b = 0.0;
   for (long i = threadIdx.x; i < N; i += 1024) {
     a += log(L[i * ld + i]);
-    b = fma(y[i], alpha[i], b);
+    if (y) b = fma(y[i], alpha[i], b);
   }
   a = warp_sum(a);
   b = warp_sum(b);

@@ -1,0 +1,279 @@
+// gpc_ig.cuh -- information-gain scoring of candidate planner paths.
+//
+// Every candidate owns a "span" of rows inside one 128-row tile of the candidate-row matrices
+// (a span never straddles a tile, so all of its k x k Gram blocks come out of ONE diagonal-tile
+// DMMA contraction):
+//      rows [rs, rs + k)        the candidate's own points (fidelity = its own label)
+//      rows [rs + k, rs + 2k)   only when the query fidelity differs: the same points at pred_fid
+// Heavy steps reuse the shared DMMA mainloop (gpc_gemm.cuh):
+//      Vt   = Kx  X^T          k_vt            (L^-1 k for every candidate row)
+//      Gram = Vt_tile Vt_tile^T   k_gram_diag  (Schur complements of all candidates of a tile)
+//      Bt   = K(cand, grid) - Vt Vg^T          k_cross_cov   (log-det variant)
+//      Zt   = Bt Xg^T          k_vt again, with the grid factor
+// and the per-candidate k x k work (Cholesky, forward substitution, log sums) runs one CTA per
+// candidate out of shared memory (k_ig_seq_cand / k_ig_logdet_cand).
+//
+// replaces: GraceRIGV3.py:443-562 and PhysicalExperimentCode/GraceRIGV3.py:446-678, where each
+// candidate costs one (log-det) or k (sequential) full O((N+k)^3) GPy refits.
+#pragma once
+#include "gpc_gemm.cuh"
+
+// Gram[tile] (128 x 128, row-major, compact) = A_tile A_tile^T, A = rows [128 tile, +128) of a
+// [m_pad][ld] matrix, contraction over kdim (multiple of 16).  grid = number of tiles.
+__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_gram_diag(const double* __restrict__ A, long ld, int kdim,
+                                                                 double* __restrict__ Gram) {
+  extern __shared__ double sm[];
+  const double* At = A + (long)blockIdx.x * 128 * ld;
+  double acc[4][4][2];
+  gpcg::zero_acc(acc);
+  gpcg::mainloop<false>(At, ld, At, ld, 0, kdim, acc, sm);
+  gpcg::store_tile(Gram + (long)blockIdx.x * 128 * 128, 128, acc, 1.0, 0.0);
+}
+
+// Bt[r][j] = k(row r, grid j) - sum_n Vt[r][n] Vg[j][n]  (latent cross-covariance given the data),
+// zero for invalid candidate rows (fid < 0) and for j >= G.  grid (m_pad/128, g_pad/128).
+__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_cross_cov(const __grid_constant__ GpcHyp h,
+                                                                 const double* __restrict__ Vt,
+                                                                 const double* __restrict__ Vg, long n_pad,
+                                                                 const double* __restrict__ Xr4,
+                                                                 const double* __restrict__ Xg4, long G,
+                                                                 long g_pad, double* __restrict__ Bt) {
+  extern __shared__ double sm[];
+  const int rt = blockIdx.x, gt = blockIdx.y;
+  double acc[4][4][2];
+  gpcg::zero_acc(acc);
+  gpcg::mainloop<false>(Vt + (long)rt * 128 * n_pad, n_pad, Vg + (long)gt * 128 * n_pad, n_pad, 0, (int)n_pad, acc,
+                        sm);
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const long r = (long)rt * 128 + gpcg::acc_row(f);
+    const double ax = Xr4[r * 4], ay = Xr4[r * 4 + 1], az = Xr4[r * 4 + 2], af = Xr4[r * 4 + 3];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double2 v;
+      double* ve = &v.x;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long j = (long)gt * 128 + gpcg::acc_col(g) + e;
+        double o = 0.0;
+        if (af >= 0.0 && j < G)
+          o = gpc_kval(h, ax, ay, az, af, Xg4[j * 4], Xg4[j * 4 + 1], Xg4[j * 4 + 2], Xg4[j * 4 + 3]) -
+              acc[f][g][e];
+        ve[e] = o;
+      }
+      *reinterpret_cast<double2*>(Bt + r * g_pad + (long)gt * 128 + gpcg::acc_col(g)) = v;
+    }
+  }
+}
+
+// ---- per-candidate small-matrix helpers (shared memory, leading dimension 65) ----------------
+#define GPC_IG_LD 65
+// dynamic shared memory of the per-candidate kernels: two k x k matrices, the span's points, scratch
+constexpr int GPC_IG_SMEM = (2 * GPC_MAXK * GPC_IG_LD + 2 * GPC_MAXK * 4 + 6 + GPC_MAXK / 8) * 8;
+
+// In-place lower Cholesky of the k x k matrix S (only the lower triangle is read / written).
+// Returns false (to every thread) when a pivot is not positive.  blockDim = 128.
+__device__ __forceinline__ bool ig_chol(double* S, int k, int* flag) {
+  const int tid = threadIdx.x;
+  if (tid == 0) *flag = 0;
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (tid == 0) {
+      const double d = S[j * GPC_IG_LD + j];
+      if (!(d > 0.0)) *flag = 1;
+      S[j * GPC_IG_LD + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double inv = 1.0 / S[j * GPC_IG_LD + j];
+    __syncthreads();
+    for (int i = j + 1 + tid; i < k; i += blockDim.x) S[i * GPC_IG_LD + j] *= inv;
+    __syncthreads();
+    // trailing update of the lower triangle, one thread per (i, l) with j < l <= i < k
+    const int m = k - j - 1;
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      const int i = j + 1 + e / m, l = j + 1 + e % m;
+      if (l <= i) S[i * GPC_IG_LD + l] = fma(-S[i * GPC_IG_LD + j], S[l * GPC_IG_LD + j], S[i * GPC_IG_LD + l]);
+    }
+    __syncthreads();
+  }
+  return *flag == 0;
+}
+
+__device__ __forceinline__ double ig_block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sequential information gain of one candidate (one CTA, 128 threads):
+//   I = sum_i log(1 + (max(lat_i, 1e-15) + noise_q) / sig_n)
+//   lat_i = q_i - sum_{j in cond, j < i or (j == i and pre_i)} W[j][i]^2,  W = chol(S)^-1 cross
+// with S the noise-inclusive Schur complement of the conditioned candidate rows (targets are
+// zero, so only covariances matter), cross[j][i] = cov(f(c_j), f(p_i) | data), q_i = var(f(p_i) | data).
+// rowmask bit0 = the row is conditioned on by later rows, bit1 = the row is appended before it
+// is predicted itself (GraceRIGV3.py:454-455; windowed variants :486-501, :547-556).
+//   span[c] = {row start, k, has separate query rows}
+// replaces: calcPathInfoSF2/SF3 (k refits), calculatePathInfoEmu (k refits, query at fidelity 0).
+// ------------------------------------------------------------------------------------------
+struct GpcSpan {
+  int rs;    // first row of the span in the padded candidate-row matrices
+  int k;     // number of points
+  int pred;  // 1: rows [rs + k, rs + 2k) hold the query copies
+  int pad;
+};
+
+__global__ void __launch_bounds__(128) k_ig_seq_cand(const __grid_constant__ GpcHyp h,
+                                                     const GpcSpan* __restrict__ spans,
+                                                     const double* __restrict__ Xr4,
+                                                     const double* __restrict__ Gram,
+                                                     const unsigned char* __restrict__ rowmask, double sig_n,
+                                                     double* __restrict__ I_out) {
+  extern __shared__ double dsm[];
+  double* S = dsm;
+  double* Cr = S + GPC_MAXK * GPC_IG_LD;
+  double(*pt)[4] = reinterpret_cast<double(*)[4]>(Cr + GPC_MAXK * GPC_IG_LD);
+  double* red = Cr + GPC_MAXK * GPC_IG_LD + 2 * GPC_MAXK * 4;
+  int* flagp = reinterpret_cast<int*>(red + 4);
+  unsigned char* msk = reinterpret_cast<unsigned char*>(red + 6);
+  const GpcSpan sp = spans[blockIdx.x];
+  const int k = sp.k, tid = threadIdx.x;
+  if (k == 0) {
+    if (tid == 0) I_out[blockIdx.x] = 0.0;
+    return;
+  }
+  const int tile = sp.rs >> 7, r0 = sp.rs & 127;
+  const double* Gt = Gram + (long)tile * 128 * 128;
+  const int rows = sp.pred ? 2 * k : k;
+  for (int e = tid; e < rows * 4; e += 128) pt[e >> 2][e & 3] = Xr4[(long)(sp.rs + (e >> 2)) * 4 + (e & 3)];
+  for (int e = tid; e < k; e += 128) msk[e] = rowmask ? rowmask[sp.rs + e] : (unsigned char)1;
+  __syncthreads();
+  const int qo = sp.pred ? k : 0;  // offset of the query rows
+  for (int e = tid; e < k * k; e += 128) {
+    const int j = e / k, i = e % k;  // j: conditioned (own) row, i: query column
+    const bool cj = msk[j] & 1;
+    // cross[j][i]
+    double c = 0.0;
+    if (cj)
+      c = gpc_kval(h, pt[j][0], pt[j][1], pt[j][2], pt[j][3], pt[qo + i][0], pt[qo + i][1], pt[qo + i][2],
+                   pt[qo + i][3]) -
+          Gt[(r0 + j) * 128 + r0 + qo + i];
+    Cr[j * GPC_IG_LD + i] = c;
+    if (i <= j) {
+      double s;
+      if (cj && (msk[i] & 1)) {
+        s = gpc_kval(h, pt[j][0], pt[j][1], pt[j][2], pt[j][3], pt[i][0], pt[i][1], pt[i][2], pt[i][3]) -
+            Gt[(r0 + j) * 128 + r0 + i];
+        if (i == j) s += h.noise[gpc_fid(h, pt[j][3])] + h.jitter;
+      } else {
+        s = (i == j) ? 1.0 : 0.0;
+      }
+      S[j * GPC_IG_LD + i] = s;
+    }
+  }
+  __syncthreads();
+  const bool ok = ig_chol(S, k, flagp);
+  double term = 0.0;
+  if (tid < k) {
+    const int i = tid;
+    const int fq = gpc_fid(h, pt[qo + i][3]);
+    double lat = h.kdiag[fq] - Gt[(r0 + qo + i) * 128 + r0 + qo + i];
+    const int upto = (msk[i] & 2) ? i + 1 : i;
+    // forward substitution of column i (in place in Cr; other threads own other columns)
+    for (int j = 0; j < upto; ++j) {
+      double w = Cr[j * GPC_IG_LD + i];
+      for (int l = 0; l < j; ++l) w = fma(-S[j * GPC_IG_LD + l], Cr[l * GPC_IG_LD + i], w);
+      w /= S[j * GPC_IG_LD + j];
+      Cr[j * GPC_IG_LD + i] = w;
+      lat = fma(-w, w, lat);
+    }
+    lat = fmax(lat, 1e-15);  // GPy clips the latent marginal variance
+    term = log(1.0 + (lat + h.noise[fq]) / sig_n);
+  }
+  const double I = ig_block_sum(term, red);
+  if (tid == 0) I_out[blockIdx.x] = ok ? I : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ------------------------------------------------------------------------------------------
+// Log-det information gain of one candidate on the fixed grid:
+//   I = 0.5 (logdet S - logdet T),  S = Schur complement of the candidate (noise + jitter on the
+//   diagonal), T = S - Z^T Z with Z = Lg^-1 B  (matrix-determinant lemma: equals
+//   0.5 (logdet Sigma_prior(grid) - logdet Sigma_post(grid | data u candidate))).
+// replaces: calcPathInfoSFBatch / calculatePathInfoEmuBatch (one refit + G x G determinant each).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ig_logdet_cand(const __grid_constant__ GpcHyp h,
+                                                        const GpcSpan* __restrict__ spans,
+                                                        const double* __restrict__ Xr4,
+                                                        const double* __restrict__ Gram,
+                                                        const double* __restrict__ GramZ,
+                                                        double* __restrict__ I_out) {
+  extern __shared__ double dsm[];
+  double* S = dsm;
+  double* T = S + GPC_MAXK * GPC_IG_LD;
+  double(*pt)[4] = reinterpret_cast<double(*)[4]>(T + GPC_MAXK * GPC_IG_LD);
+  double* red = T + GPC_MAXK * GPC_IG_LD + 2 * GPC_MAXK * 4;
+  int* flagp = reinterpret_cast<int*>(red + 4);
+  const GpcSpan sp = spans[blockIdx.x];
+  const int k = sp.k, tid = threadIdx.x;
+  if (k == 0) {
+    if (tid == 0) I_out[blockIdx.x] = 0.0;
+    return;
+  }
+  const int tile = sp.rs >> 7, r0 = sp.rs & 127;
+  const double* Gt = Gram + (long)tile * 128 * 128;
+  const double* Gz = GramZ + (long)tile * 128 * 128;
+  for (int e = tid; e < k * 4; e += 128) pt[e >> 2][e & 3] = Xr4[(long)(sp.rs + (e >> 2)) * 4 + (e & 3)];
+  __syncthreads();
+  for (int e = tid; e < k * k; e += 128) {
+    const int j = e / k, i = e % k;
+    if (i > j) continue;
+    double s = gpc_kval(h, pt[j][0], pt[j][1], pt[j][2], pt[j][3], pt[i][0], pt[i][1], pt[i][2], pt[i][3]) -
+               Gt[(r0 + j) * 128 + r0 + i];
+    if (i == j) s += h.noise[gpc_fid(h, pt[j][3])] + h.jitter;
+    S[j * GPC_IG_LD + i] = s;
+    T[j * GPC_IG_LD + i] = s - Gz[(r0 + j) * 128 + r0 + i];
+  }
+  __syncthreads();
+  const bool ok1 = ig_chol(S, k, flagp);
+  __syncthreads();
+  const bool ok2 = ig_chol(T, k, flagp);
+  double term = 0.0;
+  if (tid < k) term = log(S[tid * GPC_IG_LD + tid]) - log(T[tid * GPC_IG_LD + tid]);
+  const double I = ig_block_sum(term, red);
+  if (tid == 0) I_out[blockIdx.x] = (ok1 && ok2) ? I : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// best[0] = argmax_c I[c] (first index on ties, NaNs ignored; -1 when every value is NaN or C == 0).
+__global__ void __launch_bounds__(1024) k_argmax(const double* __restrict__ I, long C, long* __restrict__ best) {
+  __shared__ double sv[32];
+  __shared__ long si[32];
+  double bv = 0.0;
+  long bi = -1;
+  for (long c = threadIdx.x; c < C; c += 1024) {
+    const double v = I[c];
+    if (v == v && (bi < 0 || v > bv)) { bv = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bv = sv[threadIdx.x];
+    bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) best[0] = bi;
+  }
+}

@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) k_kstar(const __grid_constant__ GpcHyp h,
   for (int rr = 0; rr < 8; ++rr) {
     const int r = warp * 8 + rr;
     const long n = row0 + r;
-    const bool live = n < M;
     const double ax = ts[r][0], ay = ts[r][1], az = ts[r][2], af = ts[r][3];
+    const bool live = n < M && af >= 0.0;  // fidelity < 0 marks a padding row (information-gain spans)
     double mu = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
     double* krow = Kx + n * n_pad + j0;
 #pragma unroll 2
@@ -116,10 +116,14 @@ __global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_vt(const double* __restri
 }
 
 // mean[n] = sum_c meanpart[c][n];  var[n] = kdiag(fid_n) - sum_ib sumsq[ib][n]  (+clip, +noise).
+// With sx != NULL the NIGP test-input-noise term sum_d (d mean / d x_d)^2 sx_d^2 is added before
+// the floor (NIGP.py:304-324); sx is (1 x 3) when sx_rows == 1, else (M x 3).
 __global__ void __launch_bounds__(256) k_finalize_pred(const __grid_constant__ GpcHyp h,
                                                        const double* __restrict__ Xs4, long M, long m_pad,
                                                        const double* __restrict__ meanpart, int nchunks,
                                                        const double* __restrict__ sumsq, int nb,
+                                                       const double* __restrict__ gradpart,
+                                                       const double* __restrict__ sx, long sx_rows,
                                                        double* __restrict__ mean, double* __restrict__ var,
                                                        unsigned flags) {
   const long n = (long)blockIdx.x * 256 + threadIdx.x;
@@ -136,6 +140,15 @@ __global__ void __launch_bounds__(256) k_finalize_pred(const __grid_constant__ G
     double v = h.kdiag[f] - s;
     if (flags & 2u) v = fmax(v, 1e-15);
     if (flags & 1u) v += h.noise[f];
+    if (sx) {
+      const double* sr = sx + (sx_rows == 1 ? 0 : n * 3);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double g = 0.0;
+        for (int c = 0; c < nchunks; ++c) g += gradpart[((long)c * 3 + d) * m_pad + n];
+        v = fma(g * g, sr[d] * sr[d], v);
+      }
+    }
     if (flags & 8u) v = fmax(v + 1e-12, 1e-12);
     var[n] = v;
   }
@@ -156,14 +169,16 @@ __global__ void __launch_bounds__(256) k_finalize_grad(const double* __restrict_
 
 // ------------------------------------------------------------------------------------------
 // Full posterior covariance: cov(m, n) = k(xs_m, xs_n) - sum_i Vt(m, i) Vt(n, i)  (lower tiles,
-// mirrored on store).  grid (mt, mt).  replaces NIGP.py:299-301, GPy `Kxx - tdot(tmp.T)`,
-// emukit predict_covariance (+ element-wise clip).
+// mirrored on store).  grid (mt, mt).  cov has leading dimension ldc; with pad_identity the rows /
+// columns M .. m_pad-1 are written as an identity block (so the result can be factored in place).
+// replaces NIGP.py:299-301, GPy `Kxx - tdot(tmp.T)`, emukit predict_covariance (+ element-wise clip).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_cov(const __grid_constant__ GpcHyp h,
                                                            const double* __restrict__ Vt, long n_pad,
                                                            const double* __restrict__ Xs4, long M,
                                                            const double* __restrict__ extra_diag,
-                                                           double* __restrict__ cov, unsigned flags) {
+                                                           double* __restrict__ cov, long ldc, int pad_identity,
+                                                           unsigned flags) {
   extern __shared__ double sm[];
   const int nt = blockIdx.x, mt = blockIdx.y;
   if (nt > mt) return;
@@ -174,24 +189,30 @@ __global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_cov(const __grid_constant
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
     const long m = (long)mt * 128 + gpcg::acc_row(f);
-    if (m >= M) continue;
-    const double ax = Xs4[m * 4], ay = Xs4[m * 4 + 1], az = Xs4[m * 4 + 2], af = Xs4[m * 4 + 3];
+    double ax = 0, ay = 0, az = 0, af = 0;
+    if (m < M) { ax = Xs4[m * 4]; ay = Xs4[m * 4 + 1]; az = Xs4[m * 4 + 2]; af = Xs4[m * 4 + 3]; }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const long n = (long)nt * 128 + gpcg::acc_col(g) + e;
-        if (n >= M || (mt == nt && n > m)) continue;  // diagonal tiles: lower half, mirrored below
-        double v = gpc_kval(h, ax, ay, az, af, Xs4[n * 4], Xs4[n * 4 + 1], Xs4[n * 4 + 2], Xs4[n * 4 + 3]) -
-                   acc[f][g][e];
-        if (m == n) {
-          if (flags & 1u) v += h.noise[gpc_fid(h, af)];
-          if (extra_diag) v += extra_diag[m];
-          if (flags & 8u) v += 1e-12;
+        if (mt == nt && n > m) continue;  // diagonal tiles: lower half, mirrored below
+        double v;
+        if (m >= M || n >= M) {
+          if (!pad_identity) continue;
+          v = (m == n) ? 1.0 : 0.0;
+        } else {
+          v = gpc_kval(h, ax, ay, az, af, Xs4[n * 4], Xs4[n * 4 + 1], Xs4[n * 4 + 2], Xs4[n * 4 + 3]) -
+              acc[f][g][e];
+          if (m == n) {
+            if (flags & 1u) v += h.noise[gpc_fid(h, af)];
+            if (extra_diag) v += extra_diag[m];
+            if (flags & 8u) v += 1e-12;
+          }
+          if (flags & 4u) v = fmax(v, 1e-10);
         }
-        if (flags & 4u) v = fmax(v, 1e-10);
-        cov[m * M + n] = v;
-        if (m != n) cov[n * M + m] = v;
+        cov[m * ldc + n] = v;
+        if (m != n) cov[n * ldc + m] = v;
       }
     }
   }

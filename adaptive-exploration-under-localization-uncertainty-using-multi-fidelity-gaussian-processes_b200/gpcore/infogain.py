@@ -1,0 +1,203 @@
+"""Information-gain path-cost operators (the ``agent.CalcCost`` slot of the RIG planner,
+``GraceRIGV3.py:24,1099,1158``), batched on the GPU.
+
+Two layers:
+
+* array level -- ``seq_info_gain`` / ``logdet_info_gain`` score MANY candidates (lists of
+  point arrays) in one call through ``gpc_ig_seq`` / ``gpc_ig_logdet``;
+* agent level -- ``InfoGainOperators`` is a mixin with the reference's method names and
+  ``(V, E, path, dense) -> float`` signatures (``calcPathInfoSF2``, ``calcPathInfoSFBatch``,
+  ``calculatePathInfoEmu``, ``calculatePathInfoEmuBatch`` ...) plus the batched
+  ``score_many(V, E, paths)`` the 64k-candidate configuration uses.  It relies on the host
+  agent's own ``pathToTrajPoints`` (``GraceRIGV3.py:396-427``), which stays Python.
+
+What the reference does per candidate -- k (sequential) or one (log-det) full GPy refits of
+the (N+k)-point model -- becomes one shared L^-1 K* contraction plus k x k Schur-complement
+work per candidate; targets of appended points are zero, so only covariances matter.
+"""
+import numpy as np
+
+from . import _lib as L
+from .core import GPCore, to_x4
+from .gp_models import GPRegression, GPyMultiOutputWrapper
+
+COND, PRE = 1, 2          # row-mask bits of gpc_ig_seq
+LOG_DBL_MIN = np.log(np.nextafter(0, 1))   # below this np.linalg.det underflows to 0
+LOG_DBL_MAX = np.log(np.finfo(float).max)  # above this it overflows to inf
+
+
+def label_fidelity(var, fidLevs, bounded_top=False):
+    """Fidelity index of trajectory points from their localisation variance
+    (``GraceRIGV3.py:529-533``; ``bounded_top`` = the ``l3`` form of ``:508-512`` in which points
+    above ``fidLevs[2]`` or exactly on a threshold get index 0 all the same)."""
+    var = np.asarray(var, dtype=float).ravel()
+    l1 = var < fidLevs[0]
+    l2 = np.logical_and(var > fidLevs[0], var < fidLevs[1])
+    return (l1 * 2 + l2 * 1).astype(float)
+
+
+def _model_core(model):
+    """Device core (factored on the model's current data/hypers) of a mirrored model."""
+    if isinstance(model, GPyMultiOutputWrapper):
+        model = model.gpy_model
+    return model._ensure_factor(), model
+
+
+def _rows(cands, mf):
+    out = []
+    for c in cands:
+        c = np.asarray(c, dtype=float)
+        if c.size == 0:
+            out.append(np.zeros((0, 4)))
+        elif mf:
+            out.append(to_x4(c[:, :3], c[:, 3]))
+        else:
+            out.append(to_x4(c[:, :3]))
+    return out
+
+
+def seq_info_gain(model, cands, sig_n, pred_fid=-1, first_preadded=False, masks=None):
+    """I_c = sum_i log(1 + sigma^2(x_i | data u x_<i) / sig_n) for every candidate.
+
+    model: ``GPRegression`` (rows (k,3)) or the multi-fidelity wrapper (rows (k,4), fidelity last;
+    every point is queried at ``pred_fid`` when >= 0, ``calculatePathInfoEmu`` uses 0).
+    first_preadded: the first point is appended before it is predicted (``GraceRIGV3.py:454-455``).
+    masks: optional list of per-row uint8 masks (bit0 conditioned-on, bit1 pre-appended).
+    Returns (I (C,), argmax)."""
+    core, m = _model_core(model)
+    mf = not isinstance(m, GPRegression)
+    rows, offs = GPCore._ragged(_rows(cands, mf))
+    mask = None
+    if masks is not None:
+        mask = np.zeros(rows.shape[0], dtype=np.uint8)
+        if offs[-1]:
+            mask[:offs[-1]] = np.concatenate([np.asarray(x, np.uint8).ravel() for x in masks if len(x)])
+    return core.ig_seq(rows, offs, sig_n, pred_fid if mf else -1,
+                       L.IG_FIRST_PREADDED if first_preadded else 0, mask)
+
+
+def logdet_info_gain(model, grid, cands):
+    """Raw I_c = 0.5 (logdet S_prior(grid) - logdet S_post(grid | data u X_c)) for every candidate,
+    S = noise-inclusive predictive covariance.  Returns (I (C,), logdet_prior, argmax)."""
+    core, m = _model_core(model)
+    mf = not isinstance(m, GPRegression)
+    grid = np.asarray(grid, dtype=float)
+    g4 = to_x4(grid[:, :3], grid[:, 3]) if mf else to_x4(grid[:, :3])
+    rows, offs = GPCore._ragged(_rows(cands, mf))
+    return core.ig_logdet(g4, rows, offs)
+
+
+def _guarded_sf_batch(I_raw, logdet_prior, G, prior_fallback):
+    """The ``det == 0`` / ``isinf`` guards of ``calcPathInfoSFBatch``
+    (``PhysicalExperimentCode/GraceRIGV3.py:583-596``) re-expressed on log-determinants:
+    ``np.linalg.det`` returns 0 below exp(-744.4) and inf above exp(709.8)."""
+    ldp = logdet_prior
+    if ldp < LOG_DBL_MIN:
+        ldp = prior_fallback
+    elif ldp > LOG_DBL_MAX:
+        ldp = np.inf
+    ld_post = logdet_prior - 2.0 * np.asarray(I_raw)
+    ld_post = np.where(ld_post < LOG_DBL_MIN, 0.0, np.where(ld_post > LOG_DBL_MAX, np.inf, ld_post))
+    with np.errstate(invalid="ignore"):
+        I = np.maximum(0.5 * (ldp - ld_post), 0.0)
+    I = np.where(np.isinf(I), 0.0, I)
+    return I
+
+
+class InfoGainOperators:
+    """Mixin for a ``GraceAgent``-like object.  Needs: ``pathToTrajPoints(V, E, path, dense=...,
+    withVar=...)``, ``fidLevs``, ``fieldGrid``, ``sfgp`` and / or ``mfgp`` (mirrored models), and
+    the cache slot ``logDetPrior`` the planner resets per ``plan()``
+    (``PhysicalExperimentCode/GraceRIGV3.py:1314``)."""
+
+    logDetPrior = None
+
+    # -- path -> points (host, reference code) ---------------------------------------------
+    def _sf_points(self, V, E, path, dense):
+        return self.pathToTrajPoints(V, E, path, dense=dense)[:, :3]
+
+    def _mf_points(self, V, E, path, dense, bounded_top=True):
+        p = self.pathToTrajPoints(V, E, path, dense=dense, withVar=True)
+        return np.hstack([p[:, :3], label_fidelity(p[:, -1], self.fidLevs, bounded_top)[:, None]])
+
+    # -- sequential variants ------------------------------------------------------------------
+    def calcPathInfoSF2_many(self, V, E, paths, dense=True):
+        pts = [self._sf_points(V, E, p, dense) for p in paths]
+        sig_n = float(self.sfgp.Gaussian_noise.variance[0])
+        I, _ = seq_info_gain(self.sfgp, pts, sig_n, first_preadded=True)
+        I = np.array(I, dtype=float)
+        for c, p in enumerate(pts):  # reference: `if 0 in X.shape: return -np.inf` with X = pnts[1:]
+            if p.shape[0] < 2:
+                I[c] = -np.inf
+        return I
+
+    def calcPathInfoSF2(self, V, E, path, dense=True):
+        """``GraceRIGV3.py:443-466``."""
+        return float(self.calcPathInfoSF2_many(V, E, [path], dense)[0])
+
+    calcPathInfoSF3 = calcPathInfoSF2  # ``Phys/GraceRIGV3.py:471-496``: same arithmetic, cached copy
+
+    def calculatePathInfoEmu_many(self, V, E, paths, dense=False, sig_index=-1, windowed=True):
+        """``GraceRIGV3.py:525-562`` (``sig_index=-3``) / ``Phys/GraceRIGV3.py:641-678`` (``-1``).
+        windowed: once data + appended points exceed 100 the reference keeps only rows with
+        x < 5 lx and y < 5 ly -- and the point being predicted is then part of its own
+        conditioning set (``tempX`` is cut from ``allX`` after the append, ``:549-553``)."""
+        pts = [self._mf_points(V, E, p, dense, bounded_top=False) for p in paths]
+        gm = self.mfgp.gpy_model
+        sig_n = float(gm.param_array[sig_index])
+        if not windowed or gm.X.shape[0] + 1 <= 100:
+            if windowed and any(gm.X.shape[0] + len(p) > 100 for p in pts):
+                raise NotImplementedError("window switch-over inside a candidate (N <= 100) is not batched")
+            I, _ = seq_info_gain(self.mfgp, pts, sig_n, pred_fid=0)
+            return np.asarray(I)
+        lx, ly = [float(v) for v in gm.kern.kernels[0].lengthscale[:2]]
+        inwin = lambda X: np.logical_and(X[:, 0] < 5 * lx, X[:, 1] < 5 * ly)
+        wmodel = getattr(self, "_mf_window_model", None)
+        keep = inwin(gm.X)
+        stamp = (gm.param_array.tobytes(), gm._data_version)
+        if wmodel is None or getattr(self, "_mf_window_stamp", None) != stamp:
+            wmodel = self.mfgp.copy()
+            wmodel.set_data(gm.X[keep], np.zeros((int(keep.sum()), 1)))
+            self._mf_window_model, self._mf_window_stamp = wmodel, stamp
+        masks = [np.where(inwin(p), COND | PRE, 0).astype(np.uint8) for p in pts]
+        I, _ = seq_info_gain(wmodel, pts, sig_n, pred_fid=0, masks=masks)
+        return np.asarray(I)
+
+    def calculatePathInfoEmu(self, V, E, path, dense=False, sig_index=-1):
+        return float(self.calculatePathInfoEmu_many(V, E, [path], dense, sig_index)[0])
+
+    # -- log-det variants ---------------------------------------------------------------------
+    def calcPathInfoSFBatch_many(self, V, E, paths, dense=True):
+        """``Phys/GraceRIGV3.py:571-597`` for many paths, each scored against the agent's current
+        data (the reference's cumulative append across calls, ``:590``, is a bug of its cached
+        copy and is not reproduced)."""
+        pts = [self._sf_points(V, E, p, dense)[1:] for p in paths]
+        I_raw, ldp, _ = logdet_info_gain(self.sfgp, self.fieldGrid, pts)
+        G = np.asarray(self.fieldGrid).shape[0]
+        fallback = G * np.log(float(self.sfgp.kern.variance[0]) + float(self.sfgp.Gaussian_noise.variance[0]))
+        if self.logDetPrior is None:
+            self.logDetPrior = ldp if LOG_DBL_MIN <= ldp <= LOG_DBL_MAX else (fallback if ldp < LOG_DBL_MIN else np.inf)
+        return _guarded_sf_batch(I_raw, ldp, G, fallback)
+
+    def calcPathInfoSFBatch(self, V, E, path, dense=True):
+        return float(self.calcPathInfoSFBatch_many(V, E, [path], dense)[0])
+
+    def calculatePathInfoEmuBatch_many(self, V, E, paths, dense=False):
+        """``Phys/GraceRIGV3.py:599-618``: grid at fidelity 2, no guards, no clamp."""
+        pts = [self._mf_points(V, E, p, dense, bounded_top=True) for p in paths]
+        grid = np.asarray(self.fieldGrid, dtype=float)
+        grid4 = np.hstack([grid[:, :3], 2 * np.ones((grid.shape[0], 1))])
+        I_raw, ldp, _ = logdet_info_gain(self.mfgp, grid4, pts)
+        if self.logDetPrior is None:
+            self.logDetPrior = ldp
+        return np.asarray(I_raw)
+
+    def calculatePathInfoEmuBatch(self, V, E, path, dense=False):
+        return float(self.calculatePathInfoEmuBatch_many(V, E, [path], dense)[0])
+
+    # -- batched operator slot ------------------------------------------------------------------
+    def score_many(self, V, E, paths, operator="calculatePathInfoEmuBatch", **kw):
+        """Score a list of candidate paths in one device pass; returns (I (C,), argmax)."""
+        I = getattr(self, operator + "_many")(V, E, paths, **kw)
+        finite = np.where(np.isnan(I), -np.inf, I)
+        return I, (int(np.argmax(finite)) if len(I) else -1)

@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- GP posterior mean+var throughput (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+Workload at the default settings = BASELINE.json configs[1]: synthetic 2-fidelity AR1 GP,
+N = 2048 training points, 100 x 100 x 100 test grid (1 M points) at the top fidelity, fixed
+hyper-parameters.  One *step* = one pass of the posterior (mean + noise-
+inclusive variance) over this rank's 1 M test points.  With --gpus N (launched under torchrun,
+one rank per GPU) the factor is computed on rank 0 and NCCL-broadcast, every rank owns its own
+1 M-point shard (weak scaling) and there is no collective inside the timed region.
+
+value     device-resident inputs / outputs (gpc_predict_dev), CUDA events on the core's stream
+e2e       the reference-facing call (GPyMultiOutputWrapper.predict) with HOST buffers: pinned
+          H2D of the test rows and D2H of mean and variance inside the timed region
+roofline  the dominant kernel (k_vt: V = L^-1 K* as a DMMA contraction), algorithmic FLOPs =
+          rows x N^2 per launch, against the cuBLAS DGEMM peak measured on this pool's B200
+          (profiles/microbench/dgemm_peak_r01.json; MEASURED_PEAKS.json carries no FP64 figure)
+cpu_baseline / --impl reference
+          the NumPy/SciPy restatement of the reference's GPy/emukit arithmetic (oracle/, "port":
+          GPy and emukit are not installable here) on the box's host cores, bounded sample
+ig        secondary: RIG log-det information-gain evals/s (BASELINE configs[3], N = 4096, F = 3,
+          65536 candidates x 32 points, G = 300 grid)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+entry.setup_path()
+
+METRIC = "GP posterior mean+var test pts/sec"
+MF2_PARAMS = np.array([4.0, 2.0, 3.0, 2.5, 1.0, 1.5, 2.0, 2.0, 0.8, 0.05, 0.02])   # var,l(3) x2, rho, noise x2
+MF3_PARAMS = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+DGEMM_PEAK_FILE = os.path.join(ROOT, "profiles", "microbench", "dgemm_peak_r01.json")
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload (seeded)
+# ------------------------------------------------------------------------------------------------
+def wrbf_field(X):
+    """Weighted-RBF scalar field of the reference's simulator (exploreSimSettings.py:74-101)."""
+    WS = np.array([[0, 10.0], [0, 20.0]]); depth = 10.0
+    p = np.array([[.7 * WS[0, 1], .7 * WS[1, 1], .5 * depth], [.3 * WS[0, 1], .2 * WS[1, 1], depth],
+                  [.1 * WS[0, 1], .9 * WS[1, 1], depth], [.6 * WS[0, 1], .1 * WS[1, 1], .3 * depth],
+                  [.1 * WS[0, 1], .1 * WS[1, 1], depth]])
+    Lm, s, w = 10.0, 0.5, 0.5 * np.array([3.0, 2.0, 1.0])
+    d2 = ((X[:, None, :] - p[None, :, :]) ** 2 * w[None, None, :]).sum(-1)
+    return Lm * np.exp(-s * d2 / 10.0).sum(1)
+
+
+def make_train(N, F, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform([0, 0, 0], [10, 20, 10], (N, 3))
+    if F == 2:
+        fid = (rng.uniform(size=N) < 0.2).astype(float)                 # 80 % low / 20 % high
+        pert = np.where(fid[:, None] == 0, 0.5, 0.05)
+    else:
+        fid = rng.integers(0, F, N).astype(float)
+        pert = np.choose(fid.astype(int), [0.5, 0.2, 0.05])[:, None]
+    y = wrbf_field(X) + rng.normal(0, 0.125, N)
+    Xobs = X + rng.normal(0, 1, (N, 3)) * pert                            # localisation error
+    return np.hstack([Xobs, fid[:, None]]), y
+
+
+def make_grid(n, fid, lo=0.0):
+    ax = [np.linspace(lo, 10, n), np.linspace(lo, 20, n), np.linspace(lo, 10, n)]
+    g = np.meshgrid(*ax)
+    P = np.array([gi.ravel("F") for gi in g]).T
+    return np.hstack([P, np.full((P.shape[0], 1), float(fid))])
+
+
+def make_candidates(C, k, F, seed=1):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform([0, 0, 0], [10, 20, 10], (C, 3))
+    d = rng.normal(0, 1, (C, 3)); d *= (rng.uniform(0.5, 2.0, (C, 1)) / np.linalg.norm(d, axis=1, keepdims=True))
+    t = np.linspace(0, 1, k)[None, :, None]
+    pts = a[:, None, :] + t * d[:, None, :]
+    var = np.linspace(0.05, 7.0, k)[None, :] * rng.uniform(0.5, 1.5, (C, 1))   # ramp crossing the thresholds
+    fl = [0.25, 2.25, 6.25]
+    fid = (var < fl[0]) * 2 + ((var > fl[0]) & (var < fl[1])) * 1
+    rows = np.concatenate([pts, fid[:, :, None].astype(float)], axis=2).reshape(C * k, 4)
+    return rows, np.arange(0, (C + 1) * k, k, dtype=np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference arithmetic)
+# ------------------------------------------------------------------------------------------------
+def cpu_posterior(N, M_sample, F, params, steps=1, warmup=0, tile=20000):
+    """Times the NumPy/SciPy restatement on host cores: K* assembly, K*^T alpha, solve_triangular,
+    diagonal variance -- the factorisation is done once outside (as on the GPU)."""
+    from oracle import gp_oracle as go
+    X4, y = make_train(N, F)
+    t0 = time.perf_counter()
+    gp = go.MFGP(X4, y, params, F=F)
+    t_factor = time.perf_counter() - t0
+    rng = np.random.default_rng(5)
+    Xs4 = np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (M_sample, 3)), np.full((M_sample, 1), F - 1.0)])
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for o in range(0, M_sample, tile):
+            gp.predict(Xs4[o:o + tile])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return M_sample * len(times) / sum(times), t_factor, sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, F = args.n_train, 2
+    M_sample = min(args.m_test, int(2e4 * 8192 / N) // 2)
+    pts_s, t_factor, t_step = cpu_posterior(N, M_sample, F, MF2_PARAMS, steps=args.steps, warmup=args.warmup)
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": pts_s, "unit": "pts/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": pts_s, "unit": "pts/s", "cores": cores, "kind": "port",
+                             "sample": "%d of %d test points per step, N=%d, factor (%.2f s) outside the step; "
+                                       "NumPy/SciPy restatement of the GPy/emukit arithmetic (neither is installable "
+                                       "offline), BLAS threads = all host cores" % (M_sample, args.m_test, N, t_factor)},
+            "e2e": {"value": pts_s, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "configs[1]: synthetic 2-fidelity AR1 (Kennedy-O'Hagan) GP, N=%d train, %d-point 3D test grid "
+                        "at the top fidelity per GPU, posterior mean + noise-inclusive variance, fixed hypers"
+                        % (args.n_train, args.m_test),
+            "n_train": args.n_train, "m_test_per_gpu": args.m_test, "fidelities": 2, "rho": 0.8,
+            "chunk_rows": args.chunk,
+            "l2": "inputs larger than L2: each launch streams a %d MB K* chunk (> 126 MB L2); the 2 x %d MB factor "
+                  "operands are meant to stay L2-resident" % (args.chunk * args.n_train * 8 // 2 ** 20,
+                                                              args.n_train * args.n_train * 8 // 2 ** 20)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import gpcore
+    from gpcore import _lib as L
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    from gpcore.GPy.kern import RBF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gpcore has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gpcore.build()
+
+    N, M, F = args.n_train, args.m_test, 2
+    X4, y = make_train(N, F)
+    n = int(round(M ** (1.0 / 3)))
+    if n ** 3 == M:
+        # every rank owns a different 1 M-point grid (shifted by a sub-cell offset) -> weak scaling
+        Xs4_host = make_grid(n, F - 1, lo=0.01 * rank)
+    else:
+        Xs4_host = np.hstack([np.random.default_rng(100 + rank).uniform([0, 0, 0], [10, 20, 10], (M, 3)),
+                              np.full((M, 1), F - 1.0)])
+
+    core = gpcore.GPCore(L.KIND_MF_AR1_RBF, F, local)
+    core.set_chunk(args.chunk)
+    core.set_hypers(MF2_PARAMS, 1e-8)
+    core.set_data(X4, y)
+    t0 = time.perf_counter()
+    if world > 1:
+        from gpcore.sharding import broadcast_factor
+        if rank == 0:
+            core.factor()
+        t_factor = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        broadcast_factor(core, 0)
+        t_bcast = time.perf_counter() - t0
+    else:
+        core.factor()
+        t_factor, t_bcast = time.perf_counter() - t0, 0.0
+
+    stream = torch.cuda.ExternalStream(core.stream())
+    dXs = torch.from_numpy(Xs4_host).cuda()
+    dmean = torch.empty(M, dtype=torch.float64, device="cuda")
+    dvar = torch.empty(M, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    flags = L.INCLUDE_NOISE | L.CLIP_DIAG
+
+    def step_dev():
+        core.predict_dev(dXs.data_ptr(), M, dmean.data_ptr(), dvar.data_ptr(), flags)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    # ---- value: device-resident -----------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    core.enable_hot_timing(True)
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    core.hot_kernel_time(reset=True)
+    l0 = core.launch_count()
+    ms = timed(step_dev, args.steps, 0)
+    launches = core.launch_count() - l0
+    hot_ms, hot_n, hot_flops = core.hot_kernel_time(reset=True)
+    core.enable_hot_timing(False)
+    clk = clocks.stop() if rank == 0 else None
+    value = world * M * args.steps / (ms * 1e-3)
+
+    # ---- e2e: reference-facing API, host buffers (pinned), copies inside the timed region ---------
+    kern = LinearMultiFidelityKernel([RBF(3, ARD=True), RBF(3, ARD=True)])
+    model = GPyLinearMultiFidelityModel(X4, y[:, None], kern, n_fidelities=F, device=local)
+    model.param_array[:] = MF2_PARAMS
+    wrap = GPyMultiOutputWrapper(model, F, n_optimization_restarts=1)
+    model._ensure_factor().set_chunk(args.chunk)
+    pinned = torch.from_numpy(Xs4_host).pin_memory()
+    Xs_pinned = pinned.numpy()
+    out = {}
+
+    def step_e2e():
+        mu, var = wrap.predict(Xs_pinned)
+        out["chk"] = float(mu[0, 0]) + float(var[-1, 0])
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    e2e = world * M * args.steps / dt
+    # parity spot check of the e2e result against the device-resident result
+    mu, var = wrap.predict(Xs_pinned[:4096])
+    assert np.allclose(mu[:, 0], dmean[:4096].cpu().numpy(), rtol=0, atol=1e-9)
+    assert np.allclose(var[:, 0], dvar[:4096].cpu().numpy(), rtol=0, atol=1e-9)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    peak, peak_src = 35.46, "fallback: cuBLAS DGEMM 8192^3 measured on this pool's B200 in round 1"
+    try:
+        pk = json.load(open(DGEMM_PEAK_FILE))
+        peak = float(pk["dgemm_8192_tflops"])
+        peak_src = "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/microbench/dgemm_peak_r01.json); " \
+                   "MEASURED_PEAKS.json has no FP64 entry"
+    except Exception:
+        pass
+    rows_per_launch = M * args.steps / max(hot_n, 1)
+    alg_flops_per_launch = rows_per_launch * float(N) * float(N)
+    avg_ms = hot_ms / max(hot_n, 1)
+    achieved = alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "k_vt<false,true> (V = L^-1 K*, FP64 DMMA, fused sum of squares)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launches": hot_n, "avg_launch_ms": avg_ms,
+                "algorithmic_flops_per_launch": alg_flops_per_launch,
+                "executed_flops_per_launch": hot_flops / max(hot_n, 1),
+                "share_of_step": hot_ms / ms}
+
+    # ---- CPU baseline (bounded sample) -------------------------------------------------------------
+    M_cpu = min(M, int(2e4 * 8192 / N) // 2)
+    cpu_pts, cpu_factor, _ = cpu_posterior(N, M_cpu, F, MF2_PARAMS, steps=1, warmup=0)
+    cpu = {"value": cpu_pts, "unit": "pts/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": "%d test points (tile of the %d-point workload), N=%d; factor %.2f s outside the sample; "
+                     "NumPy/SciPy restatement of the GPy/emukit arithmetic" % (M_cpu, M, N, cpu_factor)}
+
+    line = {"metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e, "unit": "pts/s", "h2d_bytes_per_step": int(M * 32), "d2h_bytes_per_step": int(M * 16),
+                    "api": "gpcore.emukit GPyMultiOutputWrapper.predict(X4) -> gpc_predict (host pointers, pinned)"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast}
+
+    if args.ig:
+        line["ig"] = bench_ig(args, gpcore, L, torch, local)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_ig(args, gpcore, L, torch, local):
+    """Secondary metric: RIG log-det information-gain evaluations per second (configs[3])."""
+    N, F, C, k = 4096, 3, args.ig_candidates, 32
+    X4, y = make_train(N, F, seed=3)
+    core = gpcore.GPCore(L.KIND_MF_AR1_RBF, F, local)
+    core.set_hypers(MF3_PARAMS, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    g = np.meshgrid(np.linspace(0, 10, 10), np.linspace(0, 20, 6), np.linspace(0, 10, 5))
+    grid4 = np.hstack([np.array([gi.ravel("F") for gi in g]).T, 2 * np.ones((300, 1))])
+    rows, offs = make_candidates(C, k, F)
+    core.ig_logdet(grid4, rows[:k * 256], offs[:257])     # warm-up (allocations)
+    torch.cuda.synchronize()
+    core.enable_hot_timing(True)
+    core.hot_kernel_time(reset=True)
+    t0 = time.perf_counter()
+    I, prior, best = core.ig_logdet(grid4, rows, offs)
+    dt_ld = time.perf_counter() - t0
+    hot_ms, hot_n, hot_fl = core.hot_kernel_time(reset=True)
+    t0 = time.perf_counter()
+    Is, bests = core.ig_seq(rows, offs, MF3_PARAMS[-1], pred_fid=0)
+    dt_seq = time.perf_counter() - t0
+    hot_ms2, hot_n2, hot_fl2 = core.hot_kernel_time(reset=True)
+    core.close()
+    return {"metric": "RIG info-gain evals/sec (host buffers in, scores + argmax out)", "n_train": N, "fidelities": F,
+            "candidates": C, "points_per_candidate": k, "grid": 300,
+            "logdet_evals_per_s": C / dt_ld, "seq_evals_per_s": C / dt_seq,
+            "logdet_alg_tflops": C * (k * N * N + 2.0 * k * 300 * N + k * k * N) / dt_ld / 1e12,
+            "hot_kernel_tflops_executed": (hot_fl + hot_fl2) / ((hot_ms + hot_ms2) * 1e-3) / 1e12,
+            "finite": bool(np.all(np.isfinite(I)) and np.all(np.isfinite(Is))), "best": int(best)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-train", type=int, default=2048)
+    ap.add_argument("--m-test", type=int, default=1000000)
+    ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--ig", type=int, default=1)
+    ap.add_argument("--ig-candidates", type=int, default=65536)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

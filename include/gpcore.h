@@ -99,6 +99,10 @@ int gpc_kernel_matrix(gpc_handle h, const double* Xa4, long na, const double* Xb
 /* ---- posterior (NIGP.py:269-333; GPy predict; emukit wrapper predict) ----------------------- */
 int gpc_predict(gpc_handle h, const double* Xs4, long M, double* mean, double* var, unsigned flags);
 int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags);
+/* NIGP.predict(Xs, Xs_input_noise=sx) (NIGP.py:304-324): var += sum_d (d mean / d x_d)^2 sx_d^2,
+ * fused on the device; sx is (1 x 3) when sx_rows == 1, else (M x 3) input-noise std devs. */
+int gpc_predict_noisy(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows,
+                      double* mean, double* var, unsigned flags);
 /* Full M x M posterior covariance (GPy predict(full_cov=1), emukit predict_covariance,
  * NIGP.predict(return_cov=1)); mean may be NULL.  extra_diag (M, may be NULL) is added to the
  * diagonal (NIGP's test-input noise term, NIGP.py:321-324). */
@@ -109,26 +113,36 @@ int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, doubl
 int gpc_mean_grad(gpc_handle h, const double* Xs4, long M, double* mean, double* grads);
 
 /* ---- information gain (GraceRIGV3.py:443-562, PhysicalExperimentCode/GraceRIGV3.py:571-678) - */
-/* Candidates are ragged: candidate c owns rows offsets[c] .. offsets[c+1]-1 of Xc4 (<= 64 rows).
- * Sequential IG:  I_c = sum_i log(1 + s_i / sig_n), s_i = noise-inclusive predictive variance of
- * point i (queried at fidelity pred_fid when pred_fid >= 0, else at its own fidelity) given the
- * data and the candidate's earlier points appended with zero targets.
- * best (may be NULL) receives argmax_c I_c. */
+/* Candidates are ragged: candidate c owns rows offsets[c] .. offsets[c+1]-1 of Xc4 (<= 64 rows;
+ * an empty candidate scores 0).
+ * Sequential IG (calcPathInfoSF2/SF3, calculatePathInfoEmu):
+ *   I_c = sum_i log(1 + s_i / sig_n), s_i = noise-inclusive predictive variance of point i
+ *   (queried at fidelity pred_fid when pred_fid >= 0, else at its own fidelity) given the data and
+ *   the candidate's earlier points appended with zero targets.
+ * row_mask (one byte per row of Xc4, may be NULL = every row conditioned, none pre-appended):
+ *   bit0 = later rows condition on this row; bit1 = the row is appended before it is predicted
+ *   itself (the windowed variants calcPathInfoSF/SF4, calculatePathInfoEmu once > 100 points).
+ * best (may be NULL) receives argmax_c I_c (first index on ties, -1 if C == 0). */
 int gpc_ig_seq(gpc_handle h, const double* Xc4, const long* offsets, long C, double sig_n,
-               int pred_fid, unsigned flags, double* I_out, long* best);
-/* Log-det IG on a fixed grid:  I_c = 0.5 (logdet S_prior(grid) - logdet S_post(grid | data u X_c)),
- * S = noise-inclusive predictive covariance (calcPathInfoSFBatch / calculatePathInfoEmuBatch).
- * logdet_prior (may be NULL) receives logdet S_prior. */
+               int pred_fid, unsigned flags, const unsigned char* row_mask, double* I_out, long* best);
+/* Log-det IG on a fixed grid (calcPathInfoSFBatch / calculatePathInfoEmuBatch):
+ *   I_c = 0.5 (logdet S_prior(grid) - logdet S_post(grid | data u X_c)),
+ * S = noise-inclusive predictive covariance.  The raw value is returned (the reference's
+ * max(.,0) / det==0 guards live in the Python shim).  logdet_prior (may be NULL) receives
+ * logdet S_prior.  G <= 4096. */
 int gpc_ig_logdet(gpc_handle h, const double* grid4, long G, const double* Xc4, const long* offsets,
                   long C, double* I_out, double* logdet_prior, long* best);
+/* The IG calls time their dominant kernel (the same L^-1 K* contraction) through the
+ * gpc_hot_kernel_time hooks below. */
 
 /* ---- measurement hooks ---------------------------------------------------------------------- */
 void* gpc_stream(gpc_handle h);                 /* cudaStream_t all kernels are launched on     */
 long gpc_launch_count(gpc_handle h);            /* kernels launched by this handle so far        */
 int gpc_set_chunk(gpc_handle h, long m_chunk);  /* test points per launch batch (default 16384)  */
 /* Device time of the dominant kernel (the L^-1 K* DMMA contraction) accumulated with CUDA events
- * on gpc_stream() since the last reset, and the number of its launches. */
-int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, int reset);
+ * on gpc_stream() since the last reset, the number of its launches and the floating-point
+ * operations those launches executed (2 x multiply-adds over the padded triangular k-range). */
+int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, double* flops, int reset);
 int gpc_enable_hot_timing(gpc_handle h, int on);
 
 #ifdef __cplusplus

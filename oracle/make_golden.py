@@ -1,0 +1,161 @@
+"""Generate the committed golden fixtures under ``tests/golden/``.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs ``/root/reference``):
+
+    python oracle/make_golden.py
+
+* ``nigp_demo.npz``  -- the reference ``NIGP.py`` module, imported VERBATIM through
+  ``oracle/gpy_shim``, run on its own ``__main__`` data (seed 0, 1-D sin, N = 40,
+  ``NIGP.py:339-352``): fitted hypers, per-point noise, predictions (mean / var / cov, with and
+  without test-input noise), NLML and posterior-mean gradients at the fitted hypers.
+* ``nigp_field.npz`` -- the same reference functions on a bundled 3-D dataset
+  (``GPData_0.2_fieldMeas_0_T0_0.csv``, 709 rows, estimated positions) with hypers held fixed.
+* ``field_data.npz`` -- that dataset's columns (inputs for the SF / MF parity tests) and the
+  reference's test grids (``exploreSimSettings.py:116-119``, ``exploreExpSettings.py:164-167``).
+* ``gp_oracle.npz``  -- outputs of the NumPy restatement (``gp_oracle.py``; GPy / emukit arithmetic,
+  PARITY UNPINNED) on the same data: SF / MF predictions, covariances, information gains.  These
+  freeze the restatement so a later edit to the oracle cannot silently move the target.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def reference_nigp():
+    sys.path.insert(0, os.path.join(HERE, "gpy_shim"))
+    sys.path.insert(0, REF)
+    import NIGP as ref  # the reference module itself
+    assert os.path.realpath(ref.__file__).startswith(REF), ref.__file__
+    return ref
+
+
+def load_field(name="GPData_0.2_fieldMeas_0_T0_0.csv"):
+    path = os.path.join(REF, "Data", "TrajectoriesAndEstimates", "GPDataSets", name)
+    with open(path) as f:
+        hdr = f.readline().strip().split(",")
+        d = np.loadtxt(f, delimiter=",")
+    col = lambda *n: d[:, [hdr.index(k) for k in n]]
+    return {"t": col("t")[:, 0], "X": col("x", "y", "z"), "Xh": col("xh", "yh", "zh"),
+            "y": col("fieldVal")[:, 0], "fidLev": col("fidLev")[:, 0].astype(int)}
+
+
+def grid(specs):
+    g = np.meshgrid(*[np.linspace(a, b, n) for a, b, n in specs])
+    return np.array([gi.ravel("F") for gi in g]).T
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    warnings.simplefilter("ignore")
+    ref = reference_nigp()
+
+    # ---- (i) NIGP demo, seed 0 -------------------------------------------------------------
+    np.random.seed(0)
+    N = 40
+    X_true = np.linspace(-3, 3, N)[:, None]
+    f_true = np.sin(X_true).ravel()
+    sigma_x_true, sigma_y_true = 0.2, 0.05
+    X_noisy = X_true + sigma_x_true * np.random.randn(*X_true.shape)
+    y = f_true + sigma_y_true * np.random.randn(N)
+    m = ref.NIGP(n_restarts=2, iters=10, verbose=False)
+    m.fit(X_noisy, y)
+    Xs = np.linspace(-4, 4, 200)[:, None]
+    mean, var = m.predict(Xs)
+    _, cov = m.predict(Xs, return_cov=True)
+    _, var_in = m.predict(Xs, Xs_input_noise=m.sigma_x_)
+    _, cov_in = m.predict(Xs[:50], Xs_input_noise=np.full((50, 1), 0.1), return_cov=True)
+    fm, grads = ref.compute_post_mean_and_gradients(X_noisy, y, m.lengthscales_, m.sigma_f_, m.sigma_y_,
+                                                    noise_diag=m.noise_diag_train_)
+    log_hyp = np.log(np.concatenate([m.lengthscales_, [m.sigma_f_, m.sigma_y_], m.sigma_x_]))
+    nlml = ref.neg_log_marginal_likelihood(log_hyp, X_noisy, y, grads)
+    K = ref.SE_ARD_kernel(X_noisy, Xs, m.lengthscales_, m.sigma_f_)
+    np.savez_compressed(os.path.join(OUT, "nigp_demo.npz"), X=X_noisy, y=y, Xs=Xs,
+                        lengthscales=m.lengthscales_, sigma_f=m.sigma_f_, sigma_y=m.sigma_y_,
+                        sigma_x=m.sigma_x_, noise_diag=m.noise_diag_train_, params=m.get_params(),
+                        mean=mean, var=var, cov=cov, var_in=var_in, cov_in=cov_in,
+                        f_mean_train=fm, grads=grads, log_hyp=log_hyp, nlml=nlml, K=K)
+    print("nigp_demo: hypers", m.get_params())
+
+    # ---- (ii) NIGP on the bundled 3-D dataset, fixed hypers ------------------------------------
+    fld = load_field()
+    Xh, yv = fld["Xh"], fld["y"]
+    ls = np.array([2.0, 3.0, 2.5]); sf = 4.0; sy = 0.2; sx = np.array([0.1, 0.1, 0.05])
+    fm0, g0 = ref.compute_post_mean_and_gradients(Xh, yv, ls, sf, sy, noise_diag=None)
+    nd = np.sum(g0 ** 2 * sx[None, :] ** 2, axis=1)
+    lh = np.log(np.concatenate([ls, [sf, sy], sx]))
+    nlml_f = ref.neg_log_marginal_likelihood(lh, Xh, yv, g0)
+    nlml_f_extra = ref.neg_log_marginal_likelihood(lh, Xh, yv, g0, 0.01 * np.ones(len(yv)))
+    mm = ref.NIGP(verbose=False)
+    mm.lengthscales_, mm.sigma_f_, mm.sigma_y_, mm.sigma_x_ = ls, sf, sy, sx
+    mm.X_train_, mm.y_train_, mm.noise_diag_train_ = Xh, yv, nd
+    test = grid([[0, 10, 10], [0, 20, 20], [0, 10, 10]])     # exploreSimSettings.py:116-119
+    sub = test[::8]                                          # 250 points for the full covariance
+    mean_f, var_f = mm.predict(test)
+    _, cov_f = mm.predict(sub, return_cov=True)
+    _, var_f_in = mm.predict(test, Xs_input_noise=sx)
+    mean_only = mm.predict(sub, return_var=False)
+    np.savez_compressed(os.path.join(OUT, "nigp_field.npz"), ls=ls, sigma_f=sf, sigma_y=sy, sigma_x=sx,
+                        f_mean_train=fm0, grads=g0, noise_diag=nd, log_hyp=lh, nlml=nlml_f,
+                        nlml_extra=nlml_f_extra, mean=mean_f, var=var_f, cov_sub=cov_f, var_in=var_f_in,
+                        mean_only_sub=mean_only)
+    print("nigp_field: nlml", nlml_f)
+
+    # ---- (iii) dataset + grids ---------------------------------------------------------------
+    ig_grid = grid([[0, 10, 10], [0, 20, 6], [0, 10, 5]])    # exploreExpSettings.py:164-167 scaled to the box
+    np.savez_compressed(os.path.join(OUT, "field_data.npz"), test=test, test_sub=sub, ig_grid=ig_grid, **fld)
+
+    # ---- (iv) the NumPy restatement on the same data (freeze) ------------------------------------
+    sys.path.insert(0, ROOT)
+    from oracle import gp_oracle as go
+    sf_params = np.array([4.0, 2.0, 3.0, 2.5, 0.05])
+    gp = go.SFGP(Xh, yv, sf_params)
+    mu_sf, var_sf = gp.predict(test)
+    _, cov_sf = gp.predict(sub, full_cov=True)
+    gp32 = go.SFGP(Xh, yv, sf_params, kind=go.KIND_MAT32)
+    mu_32, var_32 = gp32.predict(test)
+    # three fidelities as GPTrainers.py:55-61: index 0 = fidLev 3 (lowest) ... index 2 = fidLev 1
+    order = [3, 2, 1]
+    X4 = np.concatenate([np.hstack([Xh[fld["fidLev"] == lv], np.full((np.sum(fld["fidLev"] == lv), 1), float(i))])
+                         for i, lv in enumerate(order)])
+    y4 = np.concatenate([yv[fld["fidLev"] == lv] for lv in order])
+    mf_params = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+    mf = go.MFGP(X4, y4, mf_params, F=3)
+    t4 = np.hstack([test, 2 * np.ones((len(test), 1))])
+    s4 = np.hstack([sub, 2 * np.ones((len(sub), 1))])
+    mu_mf, var_mf = mf.predict(t4)
+    cov_mf = mf.predict_covariance(s4)
+    mu_mf0, var_mf0 = mf.predict(np.hstack([sub, np.zeros((len(sub), 1))]))
+    rng = np.random.default_rng(7)
+    cands, cands4 = [], []
+    for c in range(12):
+        k = int(rng.integers(2, 20))
+        a = rng.uniform([0, 0, 0], [10, 20, 10]); b = a + rng.normal(0, 1.0, 3)
+        pts = a[None] + np.linspace(0, 1, k)[:, None] * (b - a)[None]
+        cands.append(pts)
+        cands4.append(np.hstack([pts, rng.integers(0, 3, (k, 1)).astype(float)]))
+    ig_sf_seq = np.array([go.ig_seq_sf_refit(gp, c, first_preadded=True) for c in cands])
+    ig_mf_seq = np.array([go.ig_seq_mf_refit(mf, c, sig_n=mf_params[-1], pred_fid=0) for c in cands4])
+    ig_sf_ld = np.array([go.ig_logdet_refit(gp, ig_grid, c) for c in cands])
+    g4 = np.hstack([ig_grid, 2 * np.ones((len(ig_grid), 1))])
+    ig_mf_ld = np.array([go.ig_logdet_refit(mf, g4, c) for c in cands4])
+    cand_rows = np.concatenate(cands4)
+    cand_off = np.cumsum([0] + [len(c) for c in cands4])
+    np.savez_compressed(os.path.join(OUT, "gp_oracle.npz"), sf_params=sf_params, mf_params=mf_params, X4=X4, y4=y4,
+                        mu_sf=mu_sf, var_sf=var_sf, cov_sf=cov_sf, mu_32=mu_32, var_32=var_32,
+                        mu_mf=mu_mf, var_mf=var_mf, cov_mf=cov_mf, mu_mf0=mu_mf0, var_mf0=var_mf0,
+                        nlml_sf=gp.f.nlml, nlml_mf=mf.f.nlml, cand_rows=cand_rows, cand_off=cand_off,
+                        ig_sf_seq=ig_sf_seq, ig_mf_seq=ig_mf_seq, ig_sf_ld=ig_sf_ld, ig_mf_ld=ig_mf_ld)
+    print("gp_oracle: ig_sf_seq", ig_sf_seq[:3], "ig_mf_ld", ig_mf_ld[:3])
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

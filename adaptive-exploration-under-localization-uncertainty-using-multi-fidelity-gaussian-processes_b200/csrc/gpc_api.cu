@@ -1,6 +1,7 @@
 // gpc_api.cu -- C ABI of libgpcore.so (see include/gpcore.h).  Host-side orchestration only:
 // every numerical step is one of the CUDA kernels in gpc_factor.cuh / gpc_predict.cuh /
 // gpc_ig.cuh; there is no CPU fallback.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -51,6 +52,7 @@ struct gpc_handle_s {
   long m_chunk = 16384;
   long launches = 0;
   std::string err;
+  std::vector<long> perm;  // internal row i holds the caller's training row perm[i]
   // model state
   DevBuf Xt, y, extra, L, X, T, alpha, vec, partial, scal, status;
   bool have_extra = false;
@@ -96,9 +98,8 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_syrk_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_linv_level, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_vt<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_vt<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_vt<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_vt<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpvt::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpvt::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_cross_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_gram_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -181,7 +182,7 @@ int ensure_pred_ws(gpc_handle h, long m_pad, bool need_vt, bool need_grad) {
   const int nchunks = (int)((np + KS_COLS - 1) / KS_COLS);
   CK(h->Kx.ensure((size_t)m_pad * np * 8));
   CK(h->meanpart.ensure((size_t)nchunks * m_pad * 8));
-  CK(h->sumsq.ensure((size_t)h->nb * m_pad * 8));
+  CK(h->sumsq.ensure((size_t)(2 * h->nb) * m_pad * 8));
   if (need_vt) CK(h->Vt.ensure((size_t)m_pad * np * 8));
   if (need_grad) CK(h->gradpart.ensure((size_t)nchunks * 3 * m_pad * 8));
   return GPC_OK;
@@ -215,12 +216,14 @@ int launch_vt_on(gpc_handle h, const double* A, const double* X, long ld, long m
     e1 = h->ev[h->ev_used++];
     CK(cudaEventRecord(e0, h->stream));
   }
-  k_vt<STORE_V, SUMSQ><<<dim3((unsigned)(m_pad / 128), (unsigned)(ld / 128)), gpcg::NTHREADS, gpcg::SMEM_BYTES,
-                         h->stream>>>(A, X, ld, (int)(ld / 128), m_pad, Vt, sumsq);
+  const int nb2 = (int)(ld / gpvt::BN);
+  k_vt<STORE_V, SUMSQ><<<dim3((unsigned)((nb2 + 1) / 2), (unsigned)(m_pad / gpvt::BM)), gpvt::NT, gpvt::SMEM_BYTES,
+                         h->stream>>>(A, X, ld, nb2, m_pad, Vt, sumsq);
   CKL();
   if (h->hot_timing) {
     CK(cudaEventRecord(e1, h->stream));
-    h->hot_flops += (double)m_pad * (double)ld * (double)(ld + 128);  // 2 * m_pad * sum_ib (ib+1) 128 * 128
+    // 2 * m_pad * 64 * sum_jb (jb+1) 64, minus the quarter of every diagonal tile that is skipped
+    h->hot_flops += (double)m_pad * (double)ld * (double)(ld + 32);
   }
   return GPC_OK;
 }
@@ -248,7 +251,7 @@ int predict_chunk(gpc_handle h, const double* dXs4, long M, double* dmean, doubl
   }
   const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
   k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(
-      h->hyp, dXs4, M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), h->nb, h->gradpart.d(),
+      h->hyp, dXs4, M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), 2 * h->nb, h->gradpart.d(),
       want_var ? d_sx : nullptr, sx_rows, dmean, want_var ? dvar : nullptr, flags);
   CKL();
   return GPC_OK;
@@ -379,10 +382,25 @@ int gpc_set_data(gpc_handle h, const double* X4, const double* y, const double* 
   if (N < 1) return fail(h, GPC_ERR_SHAPE, "N must be >= 1");
   CK(cudaSetDevice(h->device));
   const long np = round_up(N, 128);
+  // Multi-fidelity models keep their training rows sorted by fidelity (stable), so that a block of
+  // consecutive columns of K* shares one fidelity and the AR1 sum needs no per-lane branching.
+  // Every posterior quantity is invariant under this permutation; gpc_get_alpha undoes it.
+  h->perm.resize((size_t)N);
+  for (long i = 0; i < N; ++i) h->perm[(size_t)i] = i;
+  if (h->F > 1) {
+    for (long i = 0; i < N; ++i) {
+      const double f = X4[i * 4 + 3];
+      if (!(f >= 0.0) || f >= (double)h->F || f != std::floor(f))
+        return fail(h, GPC_ERR_ARG, "fidelity index must be an integer in [0, F)");
+    }
+    std::stable_sort(h->perm.begin(), h->perm.end(),
+                     [&](long a, long b) { return X4[a * 4 + 3] < X4[b * 4 + 3]; });
+  }
   std::vector<double> soa((size_t)4 * np, 0.0), yp((size_t)np, 0.0);
   for (long i = 0; i < N; ++i) {
-    for (int c = 0; c < 4; ++c) soa[(size_t)c * np + i] = X4[i * 4 + c];
-    yp[i] = y[i];
+    const long src = h->perm[(size_t)i];
+    for (int c = 0; c < 4; ++c) soa[(size_t)c * np + i] = X4[src * 4 + c];
+    yp[i] = y[src];
   }
   CK(h->Xt.ensure((size_t)4 * np * 8));
   CK(h->y.ensure((size_t)np * 8));
@@ -393,12 +411,12 @@ int gpc_set_data(gpc_handle h, const double* X4, const double* y, const double* 
   CK(cudaMemcpyAsync(h->Xt.p, soa.data(), (size_t)4 * np * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->y.p, yp.data(), (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
   h->have_extra = extra != nullptr;
+  std::vector<double> ep;
   if (extra) {
-    std::vector<double> ep((size_t)np, 0.0);
-    memcpy(ep.data(), extra, (size_t)N * 8);
+    ep.assign((size_t)np, 0.0);
+    for (long i = 0; i < N; ++i) ep[(size_t)i] = extra[h->perm[(size_t)i]];
     CK(h->extra.ensure((size_t)np * 8));
     CK(cudaMemcpyAsync(h->extra.p, ep.data(), (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
   h->N = N;
@@ -455,8 +473,10 @@ int gpc_get_alpha(gpc_handle h, double* alpha) {
   int rc = require_factor(h);
   if (rc) return rc;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(alpha, h->alpha.p, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> tmp((size_t)h->N);
+  CK(cudaMemcpyAsync(tmp.data(), h->alpha.p, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  for (long i = 0; i < h->N; ++i) alpha[h->perm[(size_t)i]] = tmp[(size_t)i];  // back to the caller's row order
   return GPC_OK;
 }
 
@@ -548,7 +568,8 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
   if (rc) return rc;
   if (M < 0 || (M > 0 && !Xs4)) return fail(h, GPC_ERR_SHAPE, "bad test set");
   if (sx && sx_rows != 1 && sx_rows != M) return fail(h, GPC_ERR_SHAPE, "input-noise array must be (1 x 3) or (M x 3)");
-  if (sx && h->F != 1) return fail(h, GPC_ERR_ARG, "input-noise correction is defined for single-fidelity kernels");
+  if (sx && (h->F != 1 || h->hyp.base != 0))
+    return fail(h, GPC_ERR_ARG, "input-noise correction is defined for the single-fidelity squared-exponential kernel");
   if (M == 0) return GPC_OK;
   CK(cudaSetDevice(h->device));
   const long mc = h->m_chunk;
@@ -625,7 +646,8 @@ int gpc_mean_grad(gpc_handle h, const double* Xs4, long M, double* mean, double*
   int rc = require_factor(h);
   if (rc) return rc;
   if (M < 1 || !Xs4 || !grads) return fail(h, GPC_ERR_SHAPE, "bad test set");
-  if (h->F != 1) return fail(h, GPC_ERR_ARG, "mean gradients are defined for single-fidelity kernels");
+  if (h->F != 1 || h->hyp.base != 0)
+    return fail(h, GPC_ERR_ARG, "mean gradients are defined for the single-fidelity squared-exponential kernel");
   CK(cudaSetDevice(h->device));
   const long mc = h->m_chunk;
   CK(h->Xs4.ensure((size_t)mc * 32));

@@ -82,7 +82,9 @@ int gpc_set_data(gpc_handle h, const double* X4, const double* y, const double* 
  * nlml = 0.5 y'alpha + 0.5 logdet + 0.5 N log(2 pi)  (NIGP.py:159-161; GPy -log_marginal). */
 int gpc_factor(gpc_handle h, double* nlml, double* logdet);
 
-/* Copies of the factor state for tests and for the multi-GPU broadcast. */
+/* Copies of the factor state for tests and for the multi-GPU broadcast.  alpha is returned in the
+ * caller's training-row order; L and L^-1 are those of the internal order, which for
+ * multi-fidelity models is the training set stably sorted by fidelity index. */
 int gpc_get_alpha(gpc_handle h, double* alpha /* N */);
 int gpc_get_chol(gpc_handle h, double* L /* N x N, lower, row-major */);
 int gpc_get_linv(gpc_handle h, double* Linv /* N x N, lower, row-major */);

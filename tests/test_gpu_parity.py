@@ -580,7 +580,7 @@ def test_hot_kernel_timing_hooks(gpcore_mod):
     core.enable_hot_timing(True)
     core.predict(np.hstack([rng.uniform(0, 10, (4096, 3)), np.zeros((4096, 1))]), 0)
     ms, n, fl = core.hot_kernel_time(reset=True)
-    assert n == 1 and ms > 0 and fl == 4096 * 512 * (512 + 128)
+    assert n == 1 and ms > 0 and fl == 4096 * 512 * (512 + 32)
     assert core.launch_count() - n0 == 3               # k_kstar, k_vt, k_finalize_pred
     assert core.stream() is not None
     core.close()

@@ -116,7 +116,7 @@ int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int
   cudaStream_t s = h->stream;
   CK(cudaMemsetAsync(d_status, 0, sizeof(int), s));
   for (int p = 0; p < nb; ++p) {
-    k_potrf_diag<<<1, 512, GPC_POTRF_SMEM, s>>>(A, X, n_pad, p, d_status);
+    k_potrf_diag<<<1, 256, GPC_POTRF_SMEM, s>>>(A, X, n_pad, p, d_status);
     CKL();
     const int m = nb - p - 1;
     if (m > 0) {
@@ -562,6 +562,11 @@ int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, dou
   return GPC_OK;
 }
 
+// Host-pointer posterior: the test rows are copied to the device in "super-chunks" of up to
+// GPC_STAGE_ROWS rows (one H2D copy, m_chunk-row launches back to back with no host sync in
+// between, one D2H copy per output), so copies and kernels queue up on the stream instead of
+// ping-ponging with the host once per launch.
+#define GPC_STAGE_ROWS (1L << 22)
 static int predict_host(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows, double* mean,
                         double* var, unsigned flags) {
   int rc = require_factor(h);
@@ -573,24 +578,29 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
   if (M == 0) return GPC_OK;
   CK(cudaSetDevice(h->device));
   const long mc = h->m_chunk;
-  CK(h->Xs4.ensure((size_t)mc * 32));
-  CK(h->mean.ensure((size_t)mc * 8));
-  CK(h->var.ensure((size_t)mc * 8));
+  const long stage = M < GPC_STAGE_ROWS ? round_up(M, 128) : GPC_STAGE_ROWS;
+  CK(h->Xs4.ensure((size_t)stage * 32));
+  CK(h->mean.ensure((size_t)stage * 8));
+  CK(h->var.ensure((size_t)stage * 8));
   if (sx) {
-    CK(h->ediag.ensure((size_t)(sx_rows == 1 ? 1 : mc) * 24));
+    CK(h->ediag.ensure((size_t)(sx_rows == 1 ? 1 : stage) * 24));
     if (sx_rows == 1) CK(cudaMemcpyAsync(h->ediag.p, sx, 24, cudaMemcpyHostToDevice, h->stream));
   }
   const bool want_var = var && !(flags & GPC_MEAN_ONLY);
-  for (long o = 0; o < M; o += mc) {
-    const long m = (M - o) < mc ? (M - o) : mc;
-    CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + o * 4, (size_t)m * 32, cudaMemcpyHostToDevice, h->stream));
+  for (long s0 = 0; s0 < M; s0 += stage) {
+    const long ms = (M - s0) < stage ? (M - s0) : stage;
+    CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + s0 * 4, (size_t)ms * 32, cudaMemcpyHostToDevice, h->stream));
     if (sx && sx_rows != 1)
-      CK(cudaMemcpyAsync(h->ediag.p, sx + o * 3, (size_t)m * 24, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = predict_chunk(h, h->Xs4.d(), m, mean ? h->mean.d() : nullptr, want_var ? h->var.d() : nullptr, flags,
-                            sx ? h->ediag.d() : nullptr, sx_rows)))
-      return rc;
-    if (mean) CK(cudaMemcpyAsync(mean + o, h->mean.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (want_var) CK(cudaMemcpyAsync(var + o, h->var.p, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(h->ediag.p, sx + s0 * 3, (size_t)ms * 24, cudaMemcpyHostToDevice, h->stream));
+    for (long o = 0; o < ms; o += mc) {
+      const long m = (ms - o) < mc ? (ms - o) : mc;
+      if ((rc = predict_chunk(h, h->Xs4.d() + o * 4, m, mean ? h->mean.d() + o : nullptr,
+                              want_var ? h->var.d() + o : nullptr, flags,
+                              sx ? h->ediag.d() + (sx_rows == 1 ? 0 : o * 3) : nullptr, sx_rows)))
+        return rc;
+    }
+    if (mean) CK(cudaMemcpyAsync(mean + s0, h->mean.p, (size_t)ms * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (want_var) CK(cudaMemcpyAsync(var + s0, h->var.p, (size_t)ms * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   return GPC_OK;

@@ -40,108 +40,158 @@ __global__ void __launch_bounds__(256) k_assemble_train(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// Diagonal block p: L_pp = chol(A_pp) and X_pp = L_pp^-1, one CTA, register-resident.
-// Thread (j = tid/4, q = tid%4) owns column j, rows i = 4s + q (s = 0..31).
-// Right-looking elimination with the pivot column broadcast through shared memory (one
-// __syncthreads per column); the inverse is a column-parallel forward substitution that only
-// needs warp shuffles.  status receives p + 1 for the first non-positive pivot.
+// Diagonal block p: L_pp = chol(A_pp) and X_pp = L_pp^-1, one CTA of 256 threads working out of
+// shared memory.  Blocked right-looking elimination with 16-column sub-blocks:
+//   (1) warp 0 factors the 16 x 16 diagonal sub-block in registers (one row per lane, pivots and
+//       multipliers exchanged by warp shuffles) and inverts it by forward substitution;
+//   (2) the rows below are solved against that inverse (one thread per row);
+//   (3) the trailing sub-matrix gets its rank-16 update in 4 x 4 register micro-tiles.
+// The inverse X_pp is then assembled block row by block row from the 16 x 16 diagonal inverses
+// (X_rc = -T_r sum_m L_rm X_mc).  X^T lives in the unused upper triangle of the same shared
+// array (leading dimension 129 leaves room for the shifted diagonal).
+// status receives p + 1 for the first non-positive pivot.
 // replaces: scipy cho_factor (NIGP.py:43,154,288) / LAPACK dpotrf inside GPy pdinv.
 // ------------------------------------------------------------------------------------------
 #define GPC_PD_LD 129
-constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 256 + 128) * 8;
+constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 7 * 256) * 8;
 
-__global__ void __launch_bounds__(512, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
+__global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
                                                        int p, int* __restrict__ status) {
   extern __shared__ double sm[];
-  double* Ls = sm;
-  double* col = sm + 128 * GPC_PD_LD;
-  double* invd = col + 256;
+  double* S = sm;                       // L in the lower triangle (incl. diagonal)
+  double* W = sm + 128 * GPC_PD_LD;     // 7 x (16 x 16) scratch for the inverse
+#define XT(i, j) S[(j) * GPC_PD_LD + (i) + 1]  // X(i, j), i >= j, stored transposed above the diagonal
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = tid >> 2, q = tid & 3;
   double* Ap = A + (long)p * 128 * ld + (long)p * 128;
   double* Xp = X + (long)p * 128 * ld + (long)p * 128;
-
-  for (int e = tid; e < 128 * 128; e += 512) {
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < 128 * 128; e += 256) {
     const int r = e >> 7, c = e & 127;
-    Ls[r * GPC_PD_LD + c] = Ap[(long)r * ld + c];
-  }
-  __syncthreads();
-  double a[32];
-#pragma unroll
-  for (int s = 0; s < 32; ++s) {
-    const int i = 4 * s + q;
-    a[s] = (i >= j) ? Ls[i * GPC_PD_LD + j] : 0.0;
+    if (c <= r) S[r * GPC_PD_LD + c] = Ap[(long)r * ld + c];
   }
   __syncthreads();
 
-  bool bad = false;
+#pragma unroll 1
+  for (int kb = 0; kb < 8; ++kb) {
+    const int c0 = kb * 16;
+    if (warp == 0) {
+      const int l = lane & 15;  // lanes 16..31 mirror lanes 0..15 (keeps every shuffle full-warp)
+      double a[16];
 #pragma unroll
-  for (int k = 0; k < 128; ++k) {
-    double* ck = col + (k & 1) * 128;
-    if (j == k) {
-      double d = __shfl_sync(0xFu << (lane & ~3), a[k >> 2], (lane & ~3) + (k & 3));
-      if (!(d > 0.0)) { bad = true; d = 1.0; }
-      const double dd = sqrt(d), inv = 1.0 / dd;
+      for (int j = 0; j < 16; ++j) a[j] = (j <= l) ? S[(c0 + l) * GPC_PD_LD + c0 + j] : 0.0;
+      bool isbad = false;
 #pragma unroll
-      for (int s = (k >> 2); s < 32; ++s) {
-        const int i = 4 * s + q;
-        if (i > k) { a[s] *= inv; ck[i] = a[s]; }
-        else if (i == k) { a[s] = dd; ck[i] = dd; }
+      for (int k = 0; k < 16; ++k) {
+        double d = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(d > 0.0)) { isbad = true; d = 1.0; }
+        const double dd = sqrt(d), inv = 1.0 / dd;
+        if (l == k) a[k] = dd;
+        else if (l > k) a[k] *= inv;
+#pragma unroll
+        for (int j = k + 1; j < 16; ++j) {
+          const double ljk = __shfl_sync(0xffffffffu, a[k], j);
+          if (l >= j) a[j] = fma(-a[k], ljk, a[j]);
+        }
+      }
+      if (isbad && lane == 0) bad = 1;
+      // inverse of the 16 x 16 factor: lane l computes column l of T
+      double x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        double sacc = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 0; m < i; ++m) sacc = fma(-__shfl_sync(0xffffffffu, a[m], i), x[m], sacc);
+        x[i] = sacc / __shfl_sync(0xffffffffu, a[i], i);
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j <= l) S[(c0 + l) * GPC_PD_LD + c0 + j] = a[j];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i >= l) XT(c0 + i, c0 + l) = x[i];
       }
     }
     __syncthreads();
-    if (j > k) {
-      const double ljk = ck[j];
+    const int r0 = c0 + 16, nrow = 128 - r0;
+    // (2) panel: L[r][c0 + c] = sum_{m <= c} A[r][c0 + m] T[c][m]
+    if (tid < nrow) {
+      const int r = r0 + tid;
+      double av[16], out[16];
 #pragma unroll
-      for (int s = (k >> 2); s < 32; ++s) {
-        const int i = 4 * s + q;
-        if (i >= j) a[s] = fma(-ck[i], ljk, a[s]);
+      for (int m = 0; m < 16; ++m) av[m] = S[r * GPC_PD_LD + c0 + m];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int m = 0; m <= c; ++m) sacc = fma(av[m], XT(c0 + c, c0 + m), sacc);
+        out[c] = sacc;
       }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) S[r * GPC_PD_LD + c0 + c] = out[c];
     }
-  }
-  if (bad) atomicCAS(status, 0, p + 1);
-
-  // L tile (zeros above the diagonal) -> shared -> global
+    __syncthreads();
+    // (3) trailing update, 4 x 4 micro-tiles of the lower triangle
+    const int nt = nrow >> 2;
+    for (int idx = tid; idx < nt * nt; idx += 256) {
+      const int ti = idx / nt, tj = idx - ti * nt;
+      if (tj > ti) continue;
+      const double* Pi = S + (r0 + 4 * ti) * GPC_PD_LD + c0;
+      const double* Pj = S + (r0 + 4 * tj) * GPC_PD_LD + c0;
+      double c[4][4];
 #pragma unroll
-  for (int s = 0; s < 32; ++s) {
-    const int i = 4 * s + q;
-    Ls[i * GPC_PD_LD + j] = (i >= j) ? a[s] : 0.0;
-    if (i == j) invd[j] = 1.0 / a[s];
-  }
-  __syncthreads();
-  for (int e = tid; e < 128 * 128; e += 512) {
-    const int r = e >> 7, c = e & 127;
-    Ap[(long)r * ld + c] = Ls[r * GPC_PD_LD + c];
-  }
-
-  // X = L^-1: thread group j solves L x = e_j
-  double x[32];
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-  for (int s = 0; s < 32; ++s) x[s] = (4 * s + q == j) ? 1.0 : 0.0;
-  const int kmin = warp * 8;  // x_k == 0 for k < j; every column of this warp has j >= 8 * warp
+        for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
+#pragma unroll 4
+      for (int m = 0; m < 16; ++m) {
+        double ai[4], aj[4];
 #pragma unroll
-  for (int k = 0; k < 128; ++k) {
-    if (k >= kmin) {
-      const double xk = __shfl_sync(0xffffffffu, x[k >> 2], (lane & ~3) + (k & 3)) * invd[k];
-      if (q == (k & 3)) x[k >> 2] = xk;
+        for (int u = 0; u < 4; ++u) { ai[u] = Pi[u * GPC_PD_LD + m]; aj[u] = Pj[u * GPC_PD_LD + m]; }
 #pragma unroll
-      for (int s = (k >> 2); s < 32; ++s) {
-        const int i = 4 * s + q;
-        if (i > k) x[s] = fma(-Ls[i * GPC_PD_LD + k], xk, x[s]);
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], aj[v], c[u][v]);
       }
-    }
-  }
-  __syncthreads();
 #pragma unroll
-  for (int s = 0; s < 32; ++s) {
-    const int i = 4 * s + q;
-    Ls[i * GPC_PD_LD + j] = (i >= j) ? x[s] : 0.0;
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int i = r0 + 4 * ti + u, j = r0 + 4 * tj + v;
+          if (j <= i) S[i * GPC_PD_LD + j] -= c[u][v];
+        }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int e = tid; e < 128 * 128; e += 512) {
+  if (bad && tid == 0) atomicCAS(status, 0, p + 1);
+
+  // X = L^-1 block row by block row:  X_rc = -T_r (sum_{m = c}^{r-1} L_rm X_mc),  T_r = X_rr
+#pragma unroll 1
+  for (int r = 1; r < 8; ++r) {
+    for (int e = tid; e < r * 256; e += 256) {
+      const int c = e >> 8, i = (e >> 4) & 15, j = e & 15;
+      const double* Lrow = S + (16 * r + i) * GPC_PD_LD;
+      double sacc = 0.0;
+      for (int t = j; t < 16; ++t) sacc = fma(Lrow[16 * c + t], XT(16 * c + t, 16 * c + j), sacc);  // m == c: X_cc lower
+      for (int k = 16 * (c + 1); k < 16 * r; ++k) sacc = fma(Lrow[k], XT(k, 16 * c + j), sacc);
+      W[e] = sacc;
+    }
+    __syncthreads();
+    for (int e = tid; e < r * 256; e += 256) {
+      const int c = e >> 8, i = (e >> 4) & 15, j = e & 15;
+      double sacc = 0.0;
+      for (int t = 0; t <= i; ++t) sacc = fma(XT(16 * r + i, 16 * r + t), W[(c << 8) + (t << 4) + j], sacc);
+      XT(16 * r + i, 16 * c + j) = -sacc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < 128 * 128; e += 256) {
     const int r = e >> 7, c = e & 127;
-    Xp[(long)r * ld + c] = Ls[r * GPC_PD_LD + c];
+    Ap[(long)r * ld + c] = (c <= r) ? S[r * GPC_PD_LD + c] : 0.0;
+    Xp[(long)r * ld + c] = (c <= r) ? XT(r, c) : 0.0;
   }
+#undef XT
 }
 
 // ------------------------------------------------------------------------------------------

@@ -247,7 +247,11 @@ class LinearMultiFidelityKernel(_Parameterized):
 
 
 def _x4_mf(X):
+    """(n, D + 1) rows with the fidelity index last -> (n, 4) rows; 3-D inputs already have the
+    device row layout (x, y, z, fid) and pass through without a copy."""
     X = np.asarray(X, dtype=float)
+    if X.ndim == 2 and X.shape[1] == 4 and X.flags["C_CONTIGUOUS"]:
+        return X
     return to_x4(X[:, :-1], X[:, -1])
 
 

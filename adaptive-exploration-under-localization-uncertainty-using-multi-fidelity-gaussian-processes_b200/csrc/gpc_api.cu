@@ -103,8 +103,10 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_cross_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_gram_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_aat_fro, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_ig_seq_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_ig_logdet_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
+  CK(cudaFuncSetAttribute(k_ig_selfgrid_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
   return GPC_OK;
 }
@@ -681,6 +683,59 @@ int gpc_mean_grad(gpc_handle h, const double* Xs4, long M, double* mean, double*
     CK(cudaMemcpyAsync(grads + o * 3, h->grads.p, (size_t)m * 24, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
+  return GPC_OK;
+}
+
+int gpc_spd_stats(gpc_handle h, const double* cov, long M, const double* e, double* quad, double* fro_inv,
+                  double* logdet) {
+  if (!h || !cov) return GPC_ERR_ARG;
+  if (M < 1 || M > 32768) return fail(h, GPC_ERR_SHAPE, "gpc_spd_stats: 1 <= M <= 32768");
+  CK(cudaSetDevice(h->device));
+  const long mp = round_up(M, 128);
+  const int mt = (int)(mp / 128);
+  CK(h->gS.ensure((size_t)mp * mp * 8));
+  CK(h->gSinv.ensure((size_t)mp * mp * 8));
+  CK(h->gT.ensure((size_t)mp * mp * 8));
+  CK(h->cand_aux.ensure(64));
+  CK(h->scal.ensure(64));
+  CK(h->gram.ensure((size_t)(mt * mt + 2 * mp) * 8));
+  cudaStream_t s = h->stream;
+  CK(cudaMemcpy2DAsync(h->gS.p, (size_t)mp * 8, cov, (size_t)M * 8, (size_t)M * 8, (size_t)M, cudaMemcpyHostToDevice, s));
+  k_pad_identity<<<dim3((unsigned)((mp + 255) / 256), (unsigned)mp), 256, 0, s>>>(h->gS.d(), M, mp);
+  CKL();
+  int* dstat = reinterpret_cast<int*>(static_cast<char*>(h->cand_aux.p) + 32);
+  int rc = factor_matrix(h, h->gS.d(), h->gSinv.d(), h->gT.d(), mp, dstat);
+  if (rc) return rc;
+  k_logdet_fit<<<1, 1024, 0, s>>>(h->gS.d(), mp, M, nullptr, nullptr, h->scal.d());
+  CKL();
+  double* part = h->gram.d();
+  double* ev = part + (size_t)mt * mt;
+  double* zv = ev + mp;
+  k_aat_fro<<<dim3(mt, mt), gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(h->gSinv.d(), mp, mt, part);
+  CKL();
+  if (e) {
+    CK(cudaMemsetAsync(ev, 0, (size_t)mp * 8, s));
+    CK(cudaMemcpyAsync(ev, e, (size_t)M * 8, cudaMemcpyHostToDevice, s));
+    k_trmv_n<<<(unsigned)((mp + 7) / 8), 256, 0, s>>>(h->gSinv.d(), mp, mp, ev, nullptr, 0.0, 1.0, zv);
+    CKL();
+    k_sumsq_vec<<<1, 1024, 0, s>>>(zv, M, h->scal.d() + 2);
+    CKL();
+  }
+  int st = 0;
+  double sc[3] = {0, 0, 0};
+  std::vector<double> hp((size_t)mt * mt);
+  CK(cudaMemcpyAsync(&st, dstat, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(sc, h->scal.p, 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hp.data(), part, (size_t)mt * mt * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (st != 0 || !std::isfinite(sc[0])) return fail(h, GPC_ERR_NOT_PD, "gpc_spd_stats: matrix not positive definite");
+  double f2 = 0.0;
+  for (int a = 0; a < mt; ++a)
+    for (int b = 0; b <= a; ++b) f2 += (a == b ? 1.0 : 2.0) * hp[(size_t)a * mt + b];
+  f2 -= (double)(mp - M);  // the identity padding block
+  if (logdet) *logdet = sc[0];
+  if (quad) *quad = e ? sc[2] : 0.0;
+  if (fro_inv) *fro_inv = std::sqrt(f2 > 0.0 ? f2 : 0.0);
   return GPC_OK;
 }
 

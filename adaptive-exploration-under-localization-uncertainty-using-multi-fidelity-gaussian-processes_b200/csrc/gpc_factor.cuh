@@ -320,3 +320,56 @@ __global__ void __launch_bounds__(1024) k_logdet_fit(const double* __restrict__ 
     if (threadIdx.x == 0) { scal[0] = 2.0 * a; scal[1] = b; }
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Evaluator helpers (GPTrainers.py:121-137: inv(SIG), Frobenius norm, e^T inv(SIG) e).
+// With X = L^-1 of SIG:  inv(SIG) = X^T X,  ||inv(SIG)||_F = ||X X^T||_F,  e^T inv(SIG) e = |X e|^2.
+// k_aat_fro: partial[at * mt + bt] = sum of squares of tile (at, bt) of X X^T (bt <= at), X lower.
+// k_pad_identity: rows / columns M .. m_pad-1 of a padded square matrix become an identity block.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_aat_fro(const double* __restrict__ X, long ld, int mt,
+                                                               double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  const int bt = blockIdx.x, at = blockIdx.y;
+  if (bt > at) {
+    if (threadIdx.x == 0) partial[at * mt + bt] = 0.0;
+    return;
+  }
+  double acc[4][4][2];
+  gpcg::zero_acc(acc);
+  gpcg::mainloop<false>(X + (long)at * 128 * ld, ld, X + (long)bt * 128 * ld, ld, 0, (bt + 1) * 128, acc, sm);
+  double s = 0.0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) s = fma(acc[f][g][0], acc[f][g][0], fma(acc[f][g][1], acc[f][g][1], s));
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < gpcg::NTHREADS / 32; ++w) t += sm[w];
+    partial[at * mt + bt] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pad_identity(double* __restrict__ A, long M, long m_pad) {
+  const long j = (long)blockIdx.x * 256 + threadIdx.x;
+  const long i = blockIdx.y;
+  if (j >= m_pad) return;
+  if (i >= M || j >= M) A[i * m_pad + j] = (i == j) ? 1.0 : 0.0;
+}
+
+// out[0] = sum_i z_i^2
+__global__ void __launch_bounds__(1024) k_sumsq_vec(const double* __restrict__ z, long n, double* __restrict__ out) {
+  __shared__ double s0[32];
+  double a = 0.0;
+  for (long i = threadIdx.x; i < n; i += 1024) a = fma(z[i], z[i], a);
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) s0[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = warp_sum(s0[threadIdx.x]);
+    if (threadIdx.x == 0) out[0] = a;
+  }
+}

@@ -247,6 +247,88 @@ __global__ void __launch_bounds__(128) k_ig_logdet_cand(const __grid_constant__ 
   if (tid == 0) I_out[blockIdx.x] = (ok1 && ok2) ? I : __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// ------------------------------------------------------------------------------------------
+// "Self-grid" log-det information gain of one candidate (calculatePathInfoEmu2,
+// GraceRIGV3.py:505-523): the evaluation grid is the candidate itself queried at pred_fid,
+//   I = 0.5 (logdet K(Xp) - logdet Sigma_post(Xp | data u candidate)),
+// K(Xp) the PRIOR kernel matrix (no noise, no data), Sigma_post the noise-inclusive predictive
+// covariance, optionally clipped element-wise at 1e-10 like emukit's predict_covariance.
+//   Sigma_post = Cpp - W^T W + noise_p I,  W = chol(S)^-1 Ccp,  S = Ccc + noise_c + jitter,
+// C.. = latent covariances given the data (kernel value minus the Gram block of L^-1 k).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ig_selfgrid_cand(const __grid_constant__ GpcHyp h,
+                                                          const GpcSpan* __restrict__ spans,
+                                                          const double* __restrict__ Xr4,
+                                                          const double* __restrict__ Gram, int clip,
+                                                          double* __restrict__ I_out) {
+  extern __shared__ double dsm[];
+  double* S = dsm;
+  double* Cr = S + GPC_MAXK * GPC_IG_LD;
+  double(*pt)[4] = reinterpret_cast<double(*)[4]>(Cr + GPC_MAXK * GPC_IG_LD);
+  double* red = Cr + GPC_MAXK * GPC_IG_LD + 2 * GPC_MAXK * 4;
+  int* flagp = reinterpret_cast<int*>(red + 4);
+  const GpcSpan sp = spans[blockIdx.x];
+  const int k = sp.k, tid = threadIdx.x;
+  if (k == 0) {
+    if (tid == 0) I_out[blockIdx.x] = 0.0;
+    return;
+  }
+  const int tile = sp.rs >> 7, r0 = sp.rs & 127;
+  const double* Gt = Gram + (long)tile * 128 * 128;
+  const int rows = sp.pred ? 2 * k : k, qo = sp.pred ? k : 0;
+  for (int e = tid; e < rows * 4; e += 128) pt[e >> 2][e & 3] = Xr4[(long)(sp.rs + (e >> 2)) * 4 + (e & 3)];
+  __syncthreads();
+  for (int e = tid; e < k * k; e += 128) {
+    const int j = e / k, i = e % k;
+    Cr[j * GPC_IG_LD + i] = gpc_kval(h, pt[j][0], pt[j][1], pt[j][2], pt[j][3], pt[qo + i][0], pt[qo + i][1],
+                                     pt[qo + i][2], pt[qo + i][3]) -
+                            Gt[(r0 + j) * 128 + r0 + qo + i];
+    if (i <= j) {
+      double sv = gpc_kval(h, pt[j][0], pt[j][1], pt[j][2], pt[j][3], pt[i][0], pt[i][1], pt[i][2], pt[i][3]) -
+                  Gt[(r0 + j) * 128 + r0 + i];
+      if (i == j) sv += h.noise[gpc_fid(h, pt[j][3])] + h.jitter;
+      S[j * GPC_IG_LD + i] = sv;
+    }
+  }
+  __syncthreads();
+  const bool ok0 = ig_chol(S, k, flagp);
+  if (tid < k) {  // W = Ls^-1 Ccp, column tid
+    const int i = tid;
+    for (int j = 0; j < k; ++j) {
+      double w = Cr[j * GPC_IG_LD + i];
+      for (int l = 0; l < j; ++l) w = fma(-S[j * GPC_IG_LD + l], Cr[l * GPC_IG_LD + i], w);
+      Cr[j * GPC_IG_LD + i] = w / S[j * GPC_IG_LD + j];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < k * k; e += 128) {  // Sigma_post (lower) into S
+    const int a = e / k, b = e % k;
+    if (b > a) continue;
+    double v = gpc_kval(h, pt[qo + a][0], pt[qo + a][1], pt[qo + a][2], pt[qo + a][3], pt[qo + b][0], pt[qo + b][1],
+                        pt[qo + b][2], pt[qo + b][3]) -
+               Gt[(r0 + qo + a) * 128 + r0 + qo + b];
+    for (int j = 0; j < k; ++j) v = fma(-Cr[j * GPC_IG_LD + a], Cr[j * GPC_IG_LD + b], v);
+    if (a == b) v += h.noise[gpc_fid(h, pt[qo + a][3])];
+    if (clip) v = fmax(v, 1e-10);
+    S[a * GPC_IG_LD + b] = v;
+  }
+  __syncthreads();
+  const bool ok1 = ig_chol(S, k, flagp);
+  double term = (tid < k) ? -log(S[tid * GPC_IG_LD + tid]) : 0.0;
+  __syncthreads();
+  for (int e = tid; e < k * k; e += 128) {  // prior kernel matrix of the query rows
+    const int a = e / k, b = e % k;
+    if (b <= a)
+      S[a * GPC_IG_LD + b] = gpc_kval(h, pt[qo + a][0], pt[qo + a][1], pt[qo + a][2], pt[qo + a][3], pt[qo + b][0],
+                                      pt[qo + b][1], pt[qo + b][2], pt[qo + b][3]);
+  }
+  __syncthreads();
+  const bool ok2 = ig_chol(S, k, flagp);
+  if (tid < k) term += log(S[tid * GPC_IG_LD + tid]);
+  const double I = ig_block_sum(term, red);
+  if (tid == 0) I_out[blockIdx.x] = (ok0 && ok1 && ok2) ? I : __longlong_as_double(0x7ff8000000000000LL);
+}
+
 // best[0] = argmax_c I[c] (first index on ties, NaNs ignored; -1 when every value is NaN or C == 0).
 __global__ void __launch_bounds__(1024) k_argmax(const double* __restrict__ I, long C, long* __restrict__ best) {
   __shared__ double sv[32];

@@ -79,7 +79,9 @@ SIGNATURES = {
     "gpc_predict_cov": (C.c_int, [_h, _dp, C.c_long, _dp, _dp, _dp, C.c_uint]),
     "gpc_mean_grad": (C.c_int, [_h, _dp, C.c_long, _dp, _dp]),
     "gpc_ig_seq": (C.c_int, [_h, _dp, _lp, C.c_long, C.c_double, C.c_int, C.c_uint, _ubp, _dp, _lp]),
+    "gpc_ig_selfgrid": (C.c_int, [_h, _dp, _lp, C.c_long, C.c_int, C.c_uint, _dp, _lp]),
     "gpc_ig_logdet": (C.c_int, [_h, _dp, C.c_long, _dp, _lp, C.c_long, _dp, _dp, _lp]),
+    "gpc_spd_stats": (C.c_int, [_h, _dp, C.c_long, _dp, _dp, _dp, _dp]),
     "gpc_stream": (C.c_void_p, [_h]),
     "gpc_launch_count": (C.c_long, [_h]),
     "gpc_set_chunk": (C.c_int, [_h, C.c_long]),

@@ -168,6 +168,16 @@ class GPCore:
                                      int(flags), L.ubptr(m), L.dptr(I), C.byref(best)))
         return I[:Cn], best.value
 
+    def ig_selfgrid(self, rows4, offsets, pred_fid=-1, clip=True):
+        rows4 = L.as_f64(rows4)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        Cn = offsets.size - 1
+        I = np.empty(max(Cn, 1))
+        best = C.c_long(-1)
+        self._ck(self.lib.gpc_ig_selfgrid(self.h, L.dptr(rows4), L.lptr(offsets), Cn, int(pred_fid),
+                                          L.CLIP_COV if clip else 0, L.dptr(I), C.byref(best)))
+        return I[:Cn], best.value
+
     def ig_logdet(self, grid4, rows4, offsets):
         grid4 = L.as_f64(grid4)
         rows4 = L.as_f64(rows4)
@@ -178,6 +188,20 @@ class GPCore:
         self._ck(self.lib.gpc_ig_logdet(self.h, L.dptr(grid4), grid4.shape[0], L.dptr(rows4), L.lptr(offsets), Cn,
                                         L.dptr(I), C.byref(prior), C.byref(best)))
         return I[:Cn], prior.value, best.value
+
+    # -- evaluator ------------------------------------------------------------------------
+    def spd_stats(self, cov, e=None):
+        """(e^T inv(cov) e, ||inv(cov)||_F, logdet cov) via a device Cholesky."""
+        cov = L.as_f64(cov)
+        M = cov.shape[0]
+        if cov.shape != (M, M):
+            raise ValueError("cov must be square")
+        ev = None if e is None else L.as_f64(e).ravel()
+        if ev is not None and ev.size != M:
+            raise ValueError("e must have M entries")
+        quad, fro, ld = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.gpc_spd_stats(self.h, L.dptr(cov), M, L.dptr(ev), C.byref(quad), C.byref(fro), C.byref(ld)))
+        return quad.value, fro.value, ld.value
 
     # -- measurement --------------------------------------------------------------------
     def stream(self):

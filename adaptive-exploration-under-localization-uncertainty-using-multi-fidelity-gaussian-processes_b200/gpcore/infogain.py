@@ -87,6 +87,14 @@ def logdet_info_gain(model, grid, cands):
     return core.ig_logdet(g4, rows, offs)
 
 
+def selfgrid_info_gain(model, cands, pred_fid=2, clip=True):
+    """``calculatePathInfoEmu2``: I_c = 0.5 (logdet K(Xp) - logdet S_post(Xp | data u X_c)) with the
+    grid Xp = the candidate's own points at ``pred_fid``.  Returns (I (C,), argmax)."""
+    core, m = _model_core(model)
+    rows, offs = GPCore._ragged(_rows(cands, True))
+    return core.ig_selfgrid(rows, offs, pred_fid, clip)
+
+
 def _guarded_sf_batch(I_raw, logdet_prior, G, prior_fallback):
     """The ``det == 0`` / ``isinf`` guards of ``calcPathInfoSFBatch``
     (``PhysicalExperimentCode/GraceRIGV3.py:583-596``) re-expressed on log-determinants:
@@ -136,6 +144,62 @@ class InfoGainOperators:
         return float(self.calcPathInfoSF2_many(V, E, [path], dense)[0])
 
     calcPathInfoSF3 = calcPathInfoSF2  # ``Phys/GraceRIGV3.py:471-496``: same arithmetic, cached copy
+
+    def _sf_windowed_many(self, V, E, paths, dense, first_windowed):
+        """Windowed sequential SF variants.  ``first_windowed=False``: ``calcPathInfoSF``
+        (``GraceRIGV3.py:468-503``) -- the first point is scored against the full data (appended
+        first), later points against rows with x < 3 lx and y < 3 ly of data + appended points
+        (themselves included).  ``first_windowed=True``: ``calcPathInfoSF4``
+        (``Phys/GraceRIGV3.py:498-534``) -- the first point too is scored against the window, and
+        it is appended twice when it lies inside it (``:512-513``)."""
+        gp = self.sfgp
+        pts = [self._sf_points(V, E, p, dense) for p in paths]
+        sig_n = float(gp.Gaussian_noise.variance[0])
+        lx, ly = [float(v) for v in gp.kern.lengthscale[:2]]
+        inwin = lambda X: np.logical_and(X[:, 0] < 3 * lx, X[:, 1] < 3 * ly)
+        N = gp.X.shape[0]
+        out = np.full(len(pts), -np.inf)
+        live = [c for c, p in enumerate(pts) if p.shape[0] >= 2]
+        if not live:
+            return out
+        keep = inwin(gp.X)
+        if N + 2 <= 100 or not keep.any():
+            raise NotImplementedError("window fallbacks (<= 100 rows, empty window) are not batched")
+        stamp = (gp.param_array.tobytes(), gp._data_version)
+        if getattr(self, "_sf_window_stamp", None) != stamp:
+            self._sf_window_model = gp.copy()
+            self._sf_window_model.set_XY(gp.X[keep], np.zeros((int(keep.sum()), 1)))
+            self._sf_window_stamp = stamp
+        wm = self._sf_window_model
+        P = [pts[c] for c in live]
+        wmask = [np.where(inwin(p), COND | PRE, 0).astype(np.uint8) for p in P]
+        heads = [p[:1] for p in P]
+        # later points: sum over all rows on the windowed model minus the first row's own term
+        I_all, _ = seq_info_gain(wm, P, sig_n, masks=wmask)
+        I_head, _ = seq_info_gain(wm, heads, sig_n, masks=[m[:1] for m in wmask])
+        rest = np.asarray(I_all) - np.asarray(I_head)
+        if first_windowed:
+            dup = [np.concatenate((h, h)) for h in heads]            # window copy (if inside) + the explicit append
+            m2 = [np.array([m[0] & COND, COND | PRE], dtype=np.uint8) for m in wmask]
+            I2, _ = seq_info_gain(wm, dup, sig_n, masks=m2)
+            I1, _ = seq_info_gain(wm, heads, sig_n, masks=[np.array([m[0] & COND], dtype=np.uint8) for m in wmask])
+            first = np.asarray(I2) - np.asarray(I1)
+        else:
+            first, _ = seq_info_gain(gp, heads, sig_n, first_preadded=True)
+        out[live] = np.asarray(first) + rest
+        return out
+
+    def calcPathInfoSF_many(self, V, E, paths, dense=True):
+        return self._sf_windowed_many(V, E, paths, dense, first_windowed=False)
+
+    def calcPathInfoSF(self, V, E, path, dense=True):
+        return float(self.calcPathInfoSF_many(V, E, [path], dense)[0])
+
+    def calcPathInfoSF4_many(self, V, E, paths, dense=True):
+        return self._sf_windowed_many(V, E, paths, dense, first_windowed=True)
+
+    def calcPathInfoSF4(self, V, E, path, dense=True):
+        return float(self.calcPathInfoSF4_many(V, E, [path], dense)[0])
 
     def calculatePathInfoEmu_many(self, V, E, paths, dense=False, sig_index=-1, windowed=True):
         """``GraceRIGV3.py:525-562`` (``sig_index=-3``) / ``Phys/GraceRIGV3.py:641-678`` (``-1``).
@@ -194,6 +258,16 @@ class InfoGainOperators:
 
     def calculatePathInfoEmuBatch(self, V, E, path, dense=False):
         return float(self.calculatePathInfoEmuBatch_many(V, E, [path], dense)[0])
+
+    def calculatePathInfoEmu2_many(self, V, E, paths, dense=False):
+        """``GraceRIGV3.py:505-523``: grid = the candidate's own points at fidelity 2, prior = the
+        kernel matrix, posterior = emukit ``predict_covariance`` (clipped at 1e-10)."""
+        pts = [self._mf_points(V, E, p, dense, bounded_top=True) for p in paths]
+        I, _ = selfgrid_info_gain(self.mfgp, pts, pred_fid=2, clip=True)
+        return np.asarray(I)
+
+    def calculatePathInfoEmu2(self, V, E, path, dense=False):
+        return float(self.calculatePathInfoEmu2_many(V, E, [path], dense)[0])
 
     # -- batched operator slot ------------------------------------------------------------------
     def score_many(self, V, E, paths, operator="calculatePathInfoEmuBatch", **kw):

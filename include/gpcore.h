@@ -134,8 +134,24 @@ int gpc_ig_seq(gpc_handle h, const double* Xc4, const long* offsets, long C, dou
  * logdet S_prior.  G <= 4096. */
 int gpc_ig_logdet(gpc_handle h, const double* grid4, long G, const double* Xc4, const long* offsets,
                   long C, double* I_out, double* logdet_prior, long* best);
+/* "Self-grid" log-det IG (calculatePathInfoEmu2, GraceRIGV3.py:505-523): the grid is the candidate
+ * itself queried at pred_fid (>= 0; < 0 = each point's own fidelity),
+ *   I_c = 0.5 (logdet K(Xp) - logdet S_post(Xp | data u X_c)),
+ * K(Xp) = prior kernel matrix (no noise), S_post = noise-inclusive predictive covariance, clipped
+ * element-wise at 1e-10 when flags has GPC_CLIP_COV (emukit predict_covariance).  NaN when a
+ * matrix is numerically not positive definite (the reference takes log(det) of an LU there). */
+int gpc_ig_selfgrid(gpc_handle h, const double* Xc4, const long* offsets, long C, int pred_fid,
+                    unsigned flags, double* I_out, long* best);
 /* The IG calls time their dominant kernel (the same L^-1 K* contraction) through the
  * gpc_hot_kernel_time hooks below. */
+
+/* ---- evaluator (GPTrainers.py:121-137) -------------------------------------------------------- */
+/* For a symmetric positive-definite M x M matrix cov (host, row-major) and a vector e (M, may be
+ * NULL): quad = e^T inv(cov) e, fro_inv = ||inv(cov)||_F, logdet = log det cov -- through one
+ * Cholesky + triangular inverse on the device instead of np.linalg.inv.  The covariance-weighted
+ * MSE of the reference is quad / fro_inv / M.  Any handle kind works; its model state is untouched. */
+int gpc_spd_stats(gpc_handle h, const double* cov, long M, const double* e, double* quad, double* fro_inv,
+                  double* logdet);
 
 /* ---- measurement hooks ---------------------------------------------------------------------- */
 void* gpc_stream(gpc_handle h);                 /* cudaStream_t all kernels are launched on     */

@@ -429,6 +429,22 @@ def ig_logdet_schur(gp, grid, Xc, noise_grid, noise_train, jitter=GPY_JITTER):
     return 0.5 * (np.linalg.slogdet(S)[1] - np.linalg.slogdet(T)[1])
 
 
+def ig_selfgrid_refit(gp, X4c, pred_fid=2, clip_cov=1e-10):
+    """``GraceRIGV3.py:505-523`` (calculatePathInfoEmu2) literally: grid = the candidate's own
+    points at fidelity ``pred_fid``; prior = kern.K(Xpred) (no noise, no data); posterior =
+    predict_covariance after appending the candidate with zero targets; log(det) via slogdet."""
+    X4c = np.asarray(X4c, float)
+    Xp = X4c.copy(); Xp[:, -1] = pred_fid
+    X0, Y0 = gp.X.copy(), gp.Y.copy()
+    try:
+        Kprior = gp.kern(Xp, Xp, same=True)
+        gp.set_data(np.concatenate((X0, X4c)), np.concatenate((Y0, np.zeros((len(X4c), 1)))))
+        Kpost = gp.predict_covariance(Xp, clip_cov=clip_cov)
+    finally:
+        gp.set_data(X0, Y0)
+    return 0.5 * (np.linalg.slogdet(Kprior)[1] - np.linalg.slogdet(Kpost)[1])
+
+
 def label_fidelity(var, fidlevs, open_top=True):
     """``GraceRIGV3.py:529-533`` (open_top) / ``:508-512`` (bounded l3): fidelity index of a
     candidate point from its localisation variance; strict inequalities, ties -> 0."""
@@ -441,4 +457,4 @@ def label_fidelity(var, fidlevs, open_top=True):
 def weighted_mse(err, cov):
     """``GPTrainers.py:121-137``: e^T (S^-1/||S^-1||_F) e / M."""
     inv = np.linalg.inv(cov)
-    return float(err.T @ (inv / np.linalg.norm(inv)) @ err) / err.shape[0]
+    return float((err.T @ (inv / np.linalg.norm(inv)) @ err).item()) / err.shape[0]

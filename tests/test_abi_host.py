@@ -129,3 +129,28 @@ def test_to_x4_and_ragged():
         to_x4(np.zeros((2, 4)))
     rows, offs = GPCore._ragged([np.ones((2, 4)), np.zeros((0, 4)), 2 * np.ones((3, 4))])
     assert list(offs) == [0, 2, 2, 5] and rows.shape == (5, 4) and rows[2, 0] == 2
+
+
+def test_trainer_io_formats(tmp_path):
+    """GPData CSV reader / fidelity split / result writers (GPTrainers.py:29-61,138-165)."""
+    from gpcore import evaluate
+    d = np.load(os.path.join(ROOT, "tests", "golden", "field_data.npz"))
+    cols = ["t", "x", "y", "z", "xh", "yh", "zh", "fieldVal", "fidLev"]
+    tab = np.column_stack([d["t"], d["X"], d["Xh"], d["y"], d["fidLev"]])
+    p = tmp_path / "GPData_test.csv"
+    np.savetxt(p, tab, delimiter=",", header=",".join(cols), comments="")
+    got = evaluate.read_gpdata_csv(str(p))
+    assert list(got) == cols and np.allclose(got["xh"], d["Xh"][:, 0]) and len(got["t"]) == np.sum(d["t"] < 3600)
+    xs, ys = evaluate.split_fidelities(got)
+    assert [len(x) for x in xs] == [int(np.sum(got["fidLev"] == lv)) for lv in (3, 2, 1)]
+    assert xs[0].shape[1] == 3 and ys[2].shape[1] == 1
+    from gpcore.emukit.multi_fidelity.convert_lists_to_array import convert_xy_lists_to_arrays
+    X4, Y = convert_xy_lists_to_arrays(xs, ys)
+    assert X4.shape == (len(got["t"]), 4) and set(np.unique(X4[:, 3])) <= {0.0, 1.0, 2.0}
+    m = tmp_path / "MSE_test.txt"
+    evaluate.write_mse_txt(str(m), {"mf": 5.2483, "sf": 5.2475}, {"mf": np.array([[0.1]]), "sf": 0.2})
+    back = evaluate.read_mse_txt(str(m))
+    assert back["RMSE mf"] == 5.2483 and back["WRMSE mf"] == 0.1 and back["WRMSE sf"] == 0.2
+    tp = d["test_sub"]
+    evaluate.write_gpres_csv(str(tmp_path / "GPRes.csv"), tp, tp[:, :1], tp[:, :1], tp[:, :1], tp[:, :1], tp[:, :1])
+    assert np.loadtxt(tmp_path / "GPRes.csv", delimiter=",", skiprows=1).shape == (len(tp), 8)

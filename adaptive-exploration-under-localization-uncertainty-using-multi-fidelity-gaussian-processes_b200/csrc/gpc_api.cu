@@ -10,6 +10,7 @@
 
 #include "../../include/gpcore.h"
 #include "gpc_factor.cuh"
+#include "gpc_grad.cuh"
 #include "gpc_ig.cuh"
 #include "gpc_predict.cuh"
 
@@ -53,8 +54,11 @@ struct gpc_handle_s {
   long launches = 0;
   std::string err;
   std::vector<long> perm;  // internal row i holds the caller's training row perm[i]
+  double rho[GPC_MAXF] = {1, 1, 1, 1};
+  double sigma_y = 0.0;
+  int n_noise = 1;
   // model state
-  DevBuf Xt, y, extra, L, X, T, alpha, vec, partial, scal, status;
+  DevBuf Xt, y, extra, L, X, T, alpha, vec, partial, scal, status, Wm, gpart;
   bool have_extra = false;
   // prediction workspaces
   DevBuf Xs4, Kx, meanpart, sumsq, gradpart, mean, var, Vt, cov, grads, ediag;
@@ -104,6 +108,7 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_cross_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_gram_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_aat_fro, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_kinv, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   CK(cudaFuncSetAttribute(k_ig_seq_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_ig_logdet_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_ig_selfgrid_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
@@ -313,7 +318,7 @@ int gpc_destroy(gpc_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
-                    &h->status, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
+                    &h->status, &h->Wm, &h->gpart, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
                     &h->cov, &h->grads, &h->ediag, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
@@ -342,6 +347,7 @@ int gpc_set_hypers(gpc_handle h, const double* p, int n, double jitter) {
     if (n != 5) return bad("NIGP hypers: expected [lx, ly, lz, sigma_f, sigma_y]");
     g.base = 0;
     for (int d = 0; d < 3; ++d) g.inv_l[0][d] = 1.0 / sqrt(1.0 / (1.0 / (p[d] * p[d])));  // inv_l=True round trip
+    h->sigma_y = p[4];
     g.var[0] = p[3];           // NIGP.py:18 passes sigma_f as the kernel variance
     g.noise[0] = p[4] * p[4];  // sigma_y is a standard deviation (NIGP.py:41)
     g.coef[0][0] = 1.0;
@@ -354,6 +360,8 @@ int gpc_set_hypers(gpc_handle h, const double* p, int n, double jitter) {
       for (int d = 0; d < 3; ++d) g.inv_l[m][d] = 1.0 / p[4 * m + 1 + d];
     }
     const double* rho = p + 4 * F;
+    for (int l = 0; l < F - 1; ++l) h->rho[l] = rho[l];
+    h->n_noise = (n == n1) ? 1 : F;
     for (int i = 0; i < F; ++i)
       for (int m = 0; m <= i; ++m) {
         double c = 1.0;
@@ -466,6 +474,80 @@ int gpc_factor(gpc_handle h, double* nlml, double* logdet) {
   h->factored = true;
   if (nlml) *nlml = h->nlml;
   if (logdet) *logdet = h->logdet;
+  return GPC_OK;
+}
+
+int gpc_nlml_grad(gpc_handle h, double* grad, int n, double* diagW) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  if (!grad) return GPC_ERR_ARG;
+  const int F = h->F;
+  const bool mf = (h->kind == GPC_MF_AR1_RBF || h->kind == GPC_MF_AR1_MAT32);
+  const int n_noise = mf ? h->n_noise : 1;
+  const int want = mf ? 4 * F + (F - 1) + n_noise : 5;
+  if (n != want) return fail(h, GPC_ERR_SHAPE, "gpc_nlml_grad: gradient length must match the hyper-parameter vector");
+  CK(cudaSetDevice(h->device));
+  const long np = h->n_pad;
+  const int nb = h->nb;
+  cudaStream_t s = h->stream;
+  CK(h->Wm.ensure((size_t)np * np * 8));
+  CK(h->T.ensure((size_t)np * np * 8));
+  CK(h->gpart.ensure(((size_t)nb * nb * GPC_NGK + GPC_NGK + (size_t)np) * 8));
+  GpcGradTab tab;
+  memset(&tab, 0, sizeof(tab));
+  for (int l = 0; l < F - 1; ++l)
+    for (int i = 0; i < F; ++i)
+      for (int m = 0; m <= i; ++m)
+        if (m <= l && l < i) {
+          double c = 1.0;
+          for (int q = m; q < i; ++q)
+            if (q != l) c *= h->rho[q];
+          tab.dcoef[l][i][m] = c;
+        }
+  k_transpose<<<dim3((unsigned)(np / 32), (unsigned)(np / 32)), 256, 0, s>>>(h->X.d(), h->T.d(), np);
+  CKL();
+  k_kinv<<<dim3(nb, nb), gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(h->T.d(), np, nb, h->Wm.d());
+  CKL();
+  double* part = h->gpart.d();
+  double* gsum = part + (size_t)nb * nb * GPC_NGK;
+  double* dW = gsum + GPC_NGK;
+  k_nlml_grad<<<dim3(nb, nb), 256, 0, s>>>(h->hyp, tab, h->Xt.d(), h->alpha.d(), h->Wm.d(), h->N, np, nb, part, dW);
+  CKL();
+  k_reduce_partial<<<GPC_NGK, 256, 0, s>>>(part, (long)nb * nb, gsum);
+  CKL();
+  double gk[GPC_NGK];
+  std::vector<double> dw((size_t)h->N), xf;
+  CK(cudaMemcpyAsync(gk, gsum, sizeof(gk), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(dw.data(), dW, (size_t)h->N * 8, cudaMemcpyDeviceToHost, s));
+  if (mf) {
+    xf.resize((size_t)h->N);
+    CK(cudaMemcpyAsync(xf.data(), h->Xt.d() + 3 * np, (size_t)h->N * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  // d/d noise_f = 1/2 sum_{i at fidelity f} W_ii
+  double tr_f[GPC_MAXF] = {0, 0, 0, 0};
+  for (long i = 0; i < h->N; ++i) tr_f[mf ? (int)xf[(size_t)i] : 0] += 0.5 * dw[(size_t)i];
+  if (mf) {
+    for (int m = 0; m < F; ++m)
+      for (int q = 0; q < 4; ++q) grad[4 * m + q] = gk[4 * m + q];
+    for (int l = 0; l < F - 1; ++l) grad[4 * F + l] = gk[4 * GPC_MAXF + l];
+    if (n_noise == 1) {
+      double t = 0.0;
+      for (int f = 0; f < F; ++f) t += tr_f[f];
+      grad[4 * F + F - 1] = t;
+    } else {
+      for (int f = 0; f < F; ++f) grad[4 * F + F - 1 + f] = tr_f[f];
+    }
+  } else if (h->kind == GPC_NIGP) {
+    for (int d = 0; d < 3; ++d) grad[d] = gk[1 + d];
+    grad[3] = gk[0];                                 // sigma_f is the kernel variance
+    grad[4] = 2.0 * h->sigma_y * tr_f[0];            // d/d sigma_y of sigma_y^2 on the diagonal
+  } else {
+    for (int q = 0; q < 4; ++q) grad[q] = gk[q];
+    grad[4] = tr_f[0];
+  }
+  if (diagW)
+    for (long i = 0; i < h->N; ++i) diagW[h->perm[(size_t)i]] = dw[(size_t)i];
   return GPC_OK;
 }
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "gpc_set_hypers": (C.c_int, [_h, _dp, C.c_int, C.c_double]),
     "gpc_set_data": (C.c_int, [_h, _dp, _dp, _dp, C.c_long]),
     "gpc_factor": (C.c_int, [_h, _dp, _dp]),
+    "gpc_nlml_grad": (C.c_int, [_h, _dp, C.c_int, _dp]),
     "gpc_get_alpha": (C.c_int, [_h, _dp]),
     "gpc_get_chol": (C.c_int, [_h, _dp]),
     "gpc_get_linv": (C.c_int, [_h, _dp]),

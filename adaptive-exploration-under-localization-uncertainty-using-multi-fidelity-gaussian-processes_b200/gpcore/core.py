@@ -76,6 +76,13 @@ class GPCore:
         self.nlml_, self.logdet_ = nlml.value, logdet.value
         return nlml.value, logdet.value
 
+    def nlml_grad(self, n_hyp, want_diag=False):
+        """Gradient of the NLML w.r.t. the flat hyper vector (and diag(Ky^-1 - alpha alpha^T))."""
+        g = np.empty(int(n_hyp))
+        d = np.empty(self.N) if want_diag else None
+        self._ck(self.lib.gpc_nlml_grad(self.h, L.dptr(g), g.size, L.dptr(d)))
+        return (g, d) if want_diag else g
+
     def alpha(self):
         a = np.empty(self.N)
         self._ck(self.lib.gpc_get_alpha(self.h, L.dptr(a)))

@@ -331,6 +331,15 @@ class _DeviceGP:
     def log_likelihood(self):
         return -self.objective_function()
 
+    def objective_function_gradients(self):
+        """d NLML / d param_array, analytic, on the device (``gpc_nlml_grad``)."""
+        core = self._ensure_factor()
+        return core.nlml_grad(self._flat_hypers().size)[self._grad_map()]
+
+    def _grad_map(self):
+        """Indices of the flat device hyper vector that correspond to ``param_array`` entries."""
+        return np.arange(self.param_array.size)
+
     # -- optimisation (host L-BFGS-B over the device NLML; softplus-transformed positives) ----
     def _free_mask(self):
         mask = np.ones(self.param_array.size, bool)
@@ -345,19 +354,16 @@ class _DeviceGP:
                 off += p.size
         return mask, bounds
 
-    def optimize(self, max_iters=1000, messages=False, **_):
+    def optimize(self, max_iters=1000, messages=False, analytic_gradients=True, **_):
         """``model.optimize()`` (``GPTrainers.py:68,84,94``): L-BFGS-B on the NLML, positive
         parameters through GPy's default Logexp (softplus) transform, fixed ones left alone.
-        Every objective evaluation is one device assembly + Cholesky; gradients by forward
-        differences in the transformed space."""
+        Every evaluation is one device assembly + Cholesky (+ the analytic gradient, about half a
+        factorisation more); ``analytic_gradients=False`` falls back to forward differences."""
         mask, bounds = self._free_mask()
         idx = np.nonzero(mask)[0]
         if idx.size == 0:
             return self
         start = self.param_array.copy()
-
-        def to_raw(theta):
-            return _softplus_inv(theta)
 
         def from_raw(x):
             th = _softplus(x)
@@ -367,17 +373,28 @@ class _DeviceGP:
             return th
 
         def f(x):
-            self.param_array[idx] = from_raw(x)
+            th = from_raw(x)
+            self.param_array[idx] = th
             try:
                 v = self.objective_function()
+                if not np.isfinite(v):
+                    raise np.linalg.LinAlgError("non-finite objective")
+                if not analytic_gradients:
+                    return v
+                g = self.objective_function_gradients()[idx] * (-np.expm1(-th))   # d softplus / dx = 1 - exp(-theta)
             except np.linalg.LinAlgError:
-                return 1e25
-            return v if np.isfinite(v) else 1e20
+                return (1e25, np.zeros(idx.size)) if analytic_gradients else 1e25
+            return v, g
 
-        x0 = to_raw(np.maximum(start[idx], 1e-12))
-        best_x, best_f = x0, f(x0)
+        x0 = _softplus_inv(np.maximum(start[idx], 1e-12))
+        best_x = x0
+        first = f(x0)
+        best_f = first[0] if analytic_gradients else first
         try:
-            res = minimize(f, x0, method="L-BFGS-B", options={"maxiter": int(max_iters), "eps": 1e-6})
+            opts = {"maxiter": int(max_iters)}
+            if not analytic_gradients:
+                opts["eps"] = 1e-6
+            res = minimize(f, x0, jac=bool(analytic_gradients), method="L-BFGS-B", options=opts)
             if res.fun < best_f:
                 best_x, best_f = res.x, res.fun
         finally:
@@ -443,6 +460,12 @@ class GPRegression(_DeviceGP):
     def _X4(self):
         return to_x4(self.X)
 
+    def objective_function_gradients(self):
+        g = self._ensure_factor().nlml_grad(5)          # [variance, lx, ly, lz, noise]
+        D, nl = self.kern.input_dim, self.kern._p_lengthscale.size
+        gl = g[1:1 + D] if nl > 1 else np.array([np.sum(g[1:1 + D])])   # one shared lengthscale: chain rule sums
+        return np.concatenate([[g[0]], gl, [g[4]]])
+
     def set_XY(self, X=None, Y=None):
         if X is not None:
             self.X = np.asarray(X, dtype=float)
@@ -497,6 +520,18 @@ class GPyLinearMultiFidelityModel(_DeviceGP):
 
     def _X4(self):
         return _x4_mf(self.X)
+
+    def objective_function_gradients(self):
+        F = self.n_fidelities
+        n_dev = 4 * F + (F - 1) + self._noise_vec().size
+        g = self._ensure_factor().nlml_grad(n_dev)
+        out = []
+        for m, k in enumerate(self.kern.kernels):       # (variance, lengthscale(D | 1)) per fidelity
+            D, nl = k.input_dim, k._p_lengthscale.size
+            gl = g[4 * m + 1:4 * m + 1 + D]
+            out += [[g[4 * m]], gl if nl > 1 else [np.sum(gl)]]
+        out += [g[4 * F:4 * F + F - 1], g[4 * F + F - 1:]]
+        return np.concatenate([np.atleast_1d(o) for o in out])
 
     def set_XY(self, X=None, Y=None):
         if X is not None:

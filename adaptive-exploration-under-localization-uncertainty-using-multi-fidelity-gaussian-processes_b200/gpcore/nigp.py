@@ -77,6 +77,33 @@ def neg_log_marginal_likelihood(log_hyp, X, y, grad_fixed, noise_diag_extra_fixe
     return float(nlml)
 
 
+def nlml_and_grad(log_hyp, X, y, grad_fixed, noise_diag_extra_fixed=None, device=0):
+    """The objective of ``NIGP.py:130-165`` together with its analytic gradient with respect to
+    the log hyper-parameters ``[log l (D), log sigma_f, log sigma_y, log sigma_x (D)]`` (the
+    reference differentiates numerically inside L-BFGS-B).  Returns (1e25, zeros) when not PD."""
+    X = np.asarray(X, dtype=float)
+    N, D = X.shape
+    log_hyp = np.asarray(log_hyp, dtype=float)
+    hyp = np.exp(log_hyp)
+    ls, sigma_f, sigma_y, sigma_x = hyp[:D], hyp[D], hyp[D + 1], hyp[D + 2:]
+    G2 = np.asarray(grad_fixed) ** 2
+    v = np.sum(G2 * (sigma_x[None, :] ** 2), axis=1)
+    if noise_diag_extra_fixed is not None:
+        v = v + noise_diag_extra_fixed
+    c = _core(device)
+    try:
+        c.set_hypers(_hyp5(ls, sigma_f, sigma_y), 1e-8)
+        c.set_data(to_x4(X), np.asarray(y, dtype=float).ravel(), v)
+        nlml, _ = c.factor()
+        g5, dW = c.nlml_grad(5, want_diag=True)
+    except (np.linalg.LinAlgError, ValueError):
+        return 1e25, np.zeros_like(log_hyp)
+    if not np.isfinite(nlml):
+        return 1e20, np.zeros_like(log_hyp)
+    grad = np.concatenate([g5[:D] * ls, [g5[3] * sigma_f, g5[4] * sigma_y], (sigma_x ** 2) * (dW @ G2)])
+    return float(nlml), grad
+
+
 def safe_obj(lh, X, y, grad_fixed, noise_diag_extra_fixed):
     """``NIGP.py:119-123``."""
     val = neg_log_marginal_likelihood(lh, X, y, grad_fixed, noise_diag_extra_fixed)
@@ -96,7 +123,8 @@ def _median_pairwise(X):
 class NIGP:
     """Same constructor, attributes and methods as the reference class (``NIGP.py:170-333``)."""
 
-    def __init__(self, n_restarts=3, iters=3, verbose=True, device=0):
+    def __init__(self, n_restarts=3, iters=3, verbose=True, device=0, analytic_grad=True):
+        self.analytic_grad = analytic_grad
         self.n_restarts = n_restarts
         self.iters = iters
         self.verbose = verbose
@@ -135,8 +163,12 @@ class NIGP:
         winner, last = None, None
         for _ in range(self.n_restarts):
             x0 = start + 0.1 * np.random.randn(*start.shape)
-            last = minimize(safe_obj, x0, args=(X, y, grads, zeros), method="L-BFGS-B", bounds=box,
-                            options={"maxiter": maxiter_opt})
+            if self.analytic_grad:   # device gradient: one factorisation (+ half) per L-BFGS-B evaluation
+                last = minimize(nlml_and_grad, x0, args=(X, y, grads, zeros, self.device), jac=True,
+                                method="L-BFGS-B", bounds=box, options={"maxiter": maxiter_opt})
+            else:                    # the reference's own scheme: SciPy differentiates numerically
+                last = minimize(safe_obj, x0, args=(X, y, grads, zeros), method="L-BFGS-B", bounds=box,
+                                options={"maxiter": maxiter_opt})
             if last.fun < (1e99 if winner is None else winner.fun):
                 winner = last
         chosen = last if winner is None else winner

@@ -82,6 +82,15 @@ int gpc_set_data(gpc_handle h, const double* X4, const double* y, const double* 
  * nlml = 0.5 y'alpha + 0.5 logdet + 0.5 N log(2 pi)  (NIGP.py:159-161; GPy -log_marginal). */
 int gpc_factor(gpc_handle h, double* nlml, double* logdet);
 
+/* Analytic gradient of the NLML of the current factorisation with respect to the flat
+ * hyper-parameter vector (same order and length n as gpc_set_hypers):
+ *   d NLML / d theta = 1/2 sum_ij (Ky^-1 - alpha alpha^T)_ij dKy_ij / d theta.
+ * Replaces the numerical differentiation of the reference's fits (NIGP.py:231-239 calls the
+ * objective 2D+3 times per L-BFGS-B step; GPTrainers.py:68,84,94 optimise inside GPy).
+ * diagW (N, may be NULL) receives diag(Ky^-1 - alpha alpha^T) in the caller's row order -- what
+ * NIGP needs for the sigma_x gradient (d v_i / d sigma_x_d = 2 sigma_x_d grad_id^2). */
+int gpc_nlml_grad(gpc_handle h, double* grad, int n, double* diagW);
+
 /* Copies of the factor state for tests and for the multi-GPU broadcast.  alpha is returned in the
  * caller's training-row order; L and L^-1 are those of the internal order, which for
  * multi-fidelity models is the training set stably sorted by fidelity index. */

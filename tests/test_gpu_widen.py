@@ -133,3 +133,97 @@ def test_weighted_mse_evaluator(gpcore_mod, go):
     with pytest.raises(np.linalg.LinAlgError):
         gpcore_mod.GPCore(0, 1, 0).spd_stats(np.array([[1.0, 2.0], [2.0, 1.0]]))
     assert abs(evaluate.rmse(np.array([3.0, 4.0])) - np.sqrt(12.5)) < 1e-15
+
+
+def _fd_grad(f, p, rel=1e-6):
+    g = np.zeros_like(p)
+    for i in range(p.size):
+        h = rel * max(abs(p[i]), 1e-3)
+        a, b = p.copy(), p.copy()
+        a[i] += h; b[i] -= h
+        g[i] = (f(a) - f(b)) / (2 * h)
+    return g
+
+
+@pytest.mark.parametrize("case", ["sf_rbf", "sf_mat32", "mf3_mixed", "mf3_single", "mf2_mat32"])
+def test_analytic_nlml_gradients(gpcore_mod, go, case):
+    """gpc_nlml_grad against central differences of the ORACLE's NLML (CPU, float64)."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(51)
+    N = 260
+    if case.startswith("sf"):
+        kind, ok = (L_.KIND_SF_RBF, go.KIND_RBF) if case == "sf_rbf" else (L_.KIND_SF_MAT32, go.KIND_MAT32)
+        X = rng.uniform([0, 0, 0], [10, 20, 10], (N, 3)); y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(N)
+        p = np.array([2.0, 1.5, 2.5, 2.0, 0.07])
+        X4 = np.hstack([X, np.zeros((N, 1))]); F = 1
+        f = lambda q: go.SFGP(X, y, q, kind=ok, gram=False).f.nlml
+    else:
+        F = 2 if case == "mf2_mat32" else 3
+        ok = go.KIND_MAT32 if case == "mf2_mat32" else go.KIND_RBF
+        kind = L_.KIND_MF_AR1_MAT32 if case == "mf2_mat32" else L_.KIND_MF_AR1_RBF
+        X4 = np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (N, 3)), rng.integers(0, F, (N, 1)).astype(float)])
+        y = np.sin(X4[:, 0]) + 0.3 * X4[:, 3] + 0.1 * rng.standard_normal(N)
+        if F == 3:
+            p = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+            if case == "mf3_single":
+                p = p[:15]
+        else:
+            p = np.array([4.0, 2.0, 3.0, 2.5, 1.0, 1.5, 2.0, 2.0, 0.8, 0.05, 0.02])
+        f = lambda q: go.MFGP(X4, y, q, F=F, kind=ok, gram=False).f.nlml
+    core = gpcore_mod.GPCore(kind, F, 0)
+    core.set_hypers(p, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    g, dW = core.nlml_grad(p.size, want_diag=True)
+    want = _fd_grad(f, p)
+    assert np.max(np.abs(g - want) / np.maximum(np.abs(want), 1.0)) < 2e-6, (g, want)
+    Ky_inv_minus = np.linalg.inv((go.SFGP(X4[:, :3], y, p, kind=ok, gram=False).f.L if F == 1 else
+                                  go.MFGP(X4, y, p, F=F, kind=ok, gram=False).f.L))
+    ref = go.SFGP(X4[:, :3], y, p, kind=ok, gram=False).f if F == 1 else go.MFGP(X4, y, p, F=F, kind=ok, gram=False).f
+    Wd = np.sum(Ky_inv_minus ** 2, axis=0) - ref.alpha ** 2
+    assert normwise(dW, Wd) < 1e-8
+    core.close()
+
+
+def test_model_gradients_and_optimize(gpcore_mod, go):
+    """Mirror models: objective_function_gradients in param_array order (shared lengthscale sums the
+    per-dimension terms; fixed scale stays fixed), optimize() lowers the NLML, NIGP analytic gradient."""
+    from gpcore.GPy.kern import RBF
+    from gpcore.GPy.models import GPRegression
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    from gpcore import nigp
+    d, g = golden("field_data.npz"), golden("gp_oracle.npz")
+    X, y = d["Xh"][:300], d["y"][:300]
+    m = GPRegression(X, y[:, None], RBF(3, variance=2.0, lengthscale=1.7))     # one shared lengthscale
+    m.Gaussian_noise.variance = 0.1
+    gm = m.objective_function_gradients()
+    assert gm.shape == (3,)
+    f = lambda q: go.SFGP(X, y, np.array([q[0], q[1], q[1], q[1], q[2]]), gram=False).f.nlml
+    want = _fd_grad(f, m.param_array.copy())
+    assert np.max(np.abs(gm - want) / np.maximum(np.abs(want), 1.0)) < 2e-6
+    m2 = GPRegression(X, y[:, None], RBF(3, ARD=True))
+    f0 = m2.objective_function()
+    m2.optimize(max_iters=40)
+    assert m2.objective_function() < f0 - 1.0 and np.all(m2.param_array > 0)
+    assert np.max(np.abs(m2.objective_function_gradients())) < 5.0
+    # multi-fidelity with the scale fixed (GPTrainers.py:67) -- it must not move
+    sel = np.r_[0:80, 400:480, 600:680]
+    k = LinearMultiFidelityKernel([RBF(3, ARD=True) for _ in range(3)])
+    w = GPyMultiOutputWrapper(GPyLinearMultiFidelityModel(g["X4"][sel], g["y4"][sel, None], k, n_fidelities=3), 3, 1)
+    w.gpy_model.kern.scale.fix([1, 1])
+    f0 = w.gpy_model.objective_function()
+    w.optimize()
+    assert w.gpy_model.objective_function() < f0 - 1.0
+    assert list(w.gpy_model.kern.scale) == [1.0, 1.0]
+    # NIGP: analytic gradient w.r.t. log hypers vs central differences of the module objective
+    gd = golden("nigp_demo.npz")
+    lh = gd["log_hyp"] + 0.05
+    v, gr = nigp.nlml_and_grad(lh, gd["X"], gd["y"], gd["grads"])
+    assert abs(v - nigp.neg_log_marginal_likelihood(lh, gd["X"], gd["y"], gd["grads"])) < 1e-9
+    fd = _fd_grad(lambda q: go.nigp_nlml(q, gd["X"], gd["y"], gd["grads"], gram=False), lh, rel=1e-5)
+    assert np.max(np.abs(gr - fd) / np.maximum(np.abs(fd), 1.0)) < 1e-5, (gr, fd)
+    np.random.seed(1)
+    a = nigp.NIGP(n_restarts=1, iters=2, verbose=False).fit(gd["X"], gd["y"], maxiter_opt=50)
+    assert np.all(np.isfinite(a.get_params())) and a.predict(gd["Xs"])[1].min() >= 1e-12

@@ -44,7 +44,8 @@ std::string g_create_error;
 
 struct gpc_handle_s {
   int kind = 0, F = 1, device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, side = nullptr;   // side: look-ahead stream of the factorisation
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
   GpcHyp hyp;
   bool have_hyp = false, have_data = false, factored = false;
   long N = 0, n_pad = 0;
@@ -99,9 +100,9 @@ inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int set_gemm_attrs(gpc_handle h) {
   const int sm = gpcg::SMEM_BYTES;
-  CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_syrk_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_linv_level, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_syrk_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_linv_level, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpvt::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpvt::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -118,25 +119,49 @@ int set_gemm_attrs(gpc_handle h) {
 
 // Blocked right-looking Cholesky of the n_pad x n_pad matrix A (in place, lower) followed by the
 // triangular inverse X = L^-1 (recursive doubling, scratch T).  d_status: device int, 0 = PD.
+// Look-ahead: after the panel solve of block column p only block column p+1 of the trailing
+// matrix is updated on the main stream; the (serial, one-CTA) factorisation of diagonal block p+1
+// and its panel solve then run on the side stream while the main stream finishes the rest of the
+// rank-128 update, so the latency of the diagonal kernel hides behind the DMMA work.
 int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int* d_status) {
   const int nb = (int)(n_pad / 128);
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->stream, s2 = h->side;
   CK(cudaMemsetAsync(d_status, 0, sizeof(int), s));
+  k_potrf_diag<<<1, 256, GPC_POTRF_SMEM, s>>>(A, X, n_pad, 0, d_status);
+  CKL();
   for (int p = 0; p < nb; ++p) {
-    k_potrf_diag<<<1, 256, GPC_POTRF_SMEM, s>>>(A, X, n_pad, p, d_status);
+    const int m = nb - p - 1;  // block rows below the diagonal
+    if (m == 0) break;
+    // panel p is solved on the stream that factored its diagonal block (main for p = 0, side otherwise)
+    cudaStream_t sp = (p == 0) ? s : s2;
+    k_trsm_panel<<<2 * m, gpc64::NT, gpc64::SMEM_BYTES, sp>>>(A, X, n_pad, p, 2 * (p + 1));
     CKL();
-    const int m = nb - p - 1;
-    if (m > 0) {
-      k_trsm_panel<<<m, gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(A, X, n_pad, p);
-      CKL();
-      k_syrk_panel<<<dim3(m, m), gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(A, n_pad, p);
+    if (p > 0) {
+      CK(cudaEventRecord(h->ev_side, s2));
+      CK(cudaStreamWaitEvent(s, h->ev_side, 0));
+    }
+    // block column p+1 of the trailing matrix first ...
+    k_syrk_panel<<<dim3(2, 2 * m), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, n_pad, p, 2 * (p + 1), 2 * (p + 1));
+    CKL();
+    CK(cudaEventRecord(h->ev_main, s));
+    CK(cudaStreamWaitEvent(s2, h->ev_main, 0));
+    k_potrf_diag<<<1, 256, GPC_POTRF_SMEM, s2>>>(A, X, n_pad, p + 1, d_status);
+    CKL();
+    // ... then the rest of it, concurrently with the next diagonal block
+    if (m > 1) {
+      k_syrk_panel<<<dim3(2 * (m - 1), 2 * (m - 1)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, n_pad, p, 2 * (p + 2),
+                                                                                       2 * (p + 2));
       CKL();
     }
+  }
+  if (nb > 1) {
+    CK(cudaEventRecord(h->ev_side, s2));
+    CK(cudaStreamWaitEvent(s, h->ev_side, 0));
   }
   for (int sb = 1; sb < nb; sb *= 2) {
     const int nodes = (nb + 2 * sb - 1) / (2 * sb);
     for (int phase = 0; phase < 2; ++phase) {
-      k_linv_level<<<dim3(sb, sb, nodes), gpcg::NTHREADS, gpcg::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, sb, phase);
+      k_linv_level<<<dim3(2 * sb, 2 * sb, nodes), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, sb, phase);
       CKL();
     }
   }
@@ -297,6 +322,9 @@ int gpc_create(int kind, int F, int device, gpc_handle* out) {
   h->F = F;
   h->device = device;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     std::string m = cudaGetErrorString(e);
     delete h;
@@ -323,6 +351,9 @@ int gpc_destroy(gpc_handle h) {
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->side) cudaStreamDestroy(h->side);
   cudaStreamDestroy(h->stream);
   delete h;
   return GPC_OK;

@@ -41,34 +41,39 @@ __global__ void __launch_bounds__(256) k_assemble_train(const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------
 // Diagonal block p: L_pp = chol(A_pp) and X_pp = L_pp^-1, one CTA of 256 threads working out of
-// shared memory.  Blocked right-looking elimination with 16-column sub-blocks:
+// shared memory.  It sits on the critical path of the factorisation (nb serial launches), so it
+// is organised for latency: 8 steps over 16-column sub-blocks, three barriers each,
 //   (1) warp 0 factors the 16 x 16 diagonal sub-block in registers (one row per lane, pivots and
-//       multipliers exchanged by warp shuffles) and inverts it by forward substitution;
-//   (2) the rows below are solved against that inverse (one thread per row);
-//   (3) the trailing sub-matrix gets its rank-16 update in 4 x 4 register micro-tiles.
-// The inverse X_pp is then assembled block row by block row from the 16 x 16 diagonal inverses
-// (X_rc = -T_r sum_m L_rm X_mc).  X^T lives in the unused upper triangle of the same shared
-// array (leading dimension 129 leaves room for the shifted diagonal).
+//       multipliers exchanged by warp shuffles, rsqrt instead of sqrt + divide) and inverts it by
+//       a right-looking substitution (15 independent updates per step);
+//   (2) threads 0..111 solve the rows below against that inverse (L panel) while threads
+//       128..239 finish block row kb of the inverse, X_kb,: = T_kb Y_kb,:;
+//   (3) all threads apply rank-16 updates in 4 x 4 register micro-tiles: to the trailing
+//       sub-matrix (Cholesky) and to the running right-hand side Y of L X = I (inverse).
+// X^T (and Y before it) lives in the unused upper triangle of the same shared array: leading
+// dimension 129 leaves room for the shifted diagonal.
 // status receives p + 1 for the first non-positive pivot.
 // replaces: scipy cho_factor (NIGP.py:43,154,288) / LAPACK dpotrf inside GPy pdinv.
 // ------------------------------------------------------------------------------------------
 #define GPC_PD_LD 129
-constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 7 * 256) * 8;
+constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 8) * 8;
 
 __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
                                                        int p, int* __restrict__ status) {
   extern __shared__ double sm[];
-  double* S = sm;                       // L in the lower triangle (incl. diagonal)
-  double* W = sm + 128 * GPC_PD_LD;     // 7 x (16 x 16) scratch for the inverse
-#define XT(i, j) S[(j) * GPC_PD_LD + (i) + 1]  // X(i, j), i >= j, stored transposed above the diagonal
+  double* S = sm;  // L in the lower triangle (incl. diagonal), X^T above it
+#define XT(i, j) S[(j) * GPC_PD_LD + (i) + 1]  // X(i, j), i >= j
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* Ap = A + (long)p * 128 * ld + (long)p * 128;
   double* Xp = X + (long)p * 128 * ld + (long)p * 128;
   __shared__ int bad;
   if (tid == 0) bad = 0;
+#pragma unroll 8
   for (int e = tid; e < 128 * 128; e += 256) {
     const int r = e >> 7, c = e & 127;
-    if (c <= r) S[r * GPC_PD_LD + c] = Ap[(long)r * ld + c];
+    const double v = (c <= r) ? Ap[(long)r * ld + c] : 0.0;
+    if (c <= r) S[r * GPC_PD_LD + c] = v;
+    else S[r * GPC_PD_LD + c + 1] = 0.0;  // Y = 0 (slot of X(c, r))
   }
   __syncthreads();
 
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
     const int c0 = kb * 16;
     if (warp == 0) {
       const int l = lane & 15;  // lanes 16..31 mirror lanes 0..15 (keeps every shuffle full-warp)
-      double a[16];
+      double a[16], invd[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = (j <= l) ? S[(c0 + l) * GPC_PD_LD + c0 + j] : 0.0;
       bool isbad = false;
@@ -85,7 +90,10 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
       for (int k = 0; k < 16; ++k) {
         double d = __shfl_sync(0xffffffffu, a[k], k);
         if (!(d > 0.0)) { isbad = true; d = 1.0; }
-        const double dd = sqrt(d), inv = 1.0 / dd;
+        double inv = rsqrt(d);
+        inv = inv * fma(-0.5 * d * inv, inv, 1.5);  // one more Newton step: full double accuracy
+        const double dd = d * inv;
+        invd[k] = inv;
         if (l == k) a[k] = dd;
         else if (l > k) a[k] *= inv;
 #pragma unroll
@@ -95,14 +103,15 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
         }
       }
       if (isbad && lane == 0) bad = 1;
-      // inverse of the 16 x 16 factor: lane l computes column l of T
+      // T = L_kk^-1, column l per lane, right-looking: once x_k is final every later row is updated
       double x[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        double sacc = (i == l) ? 1.0 : 0.0;
+      for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
 #pragma unroll
-        for (int m = 0; m < i; ++m) sacc = fma(-__shfl_sync(0xffffffffu, a[m], i), x[m], sacc);
-        x[i] = sacc / __shfl_sync(0xffffffffu, a[i], i);
+      for (int k = 0; k < 16; ++k) {
+        x[k] *= invd[k];
+#pragma unroll
+        for (int i = k + 1; i < 16; ++i) x[i] = fma(-__shfl_sync(0xffffffffu, a[k], i), x[k], x[i]);
       }
       if (lane < 16) {
 #pragma unroll
@@ -115,8 +124,8 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
     }
     __syncthreads();
     const int r0 = c0 + 16, nrow = 128 - r0;
-    // (2) panel: L[r][c0 + c] = sum_{m <= c} A[r][c0 + m] T[c][m]
     if (tid < nrow) {
+      // (2a) panel: L[r][c0 + c] = sum_{m <= c} A[r][c0 + m] T[c][m]
       const int r = r0 + tid;
       double av[16], out[16];
 #pragma unroll
@@ -130,62 +139,81 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
       }
 #pragma unroll
       for (int c = 0; c < 16; ++c) S[r * GPC_PD_LD + c0 + c] = out[c];
+    } else if (tid >= 128 && tid - 128 < c0) {
+      // (2b) inverse, block row kb: X[c0 + i][j] = sum_{t <= i} T[i][t] Y[c0 + t][j],  j < c0
+      const int j = tid - 128;
+      double yv[16], out[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) yv[t] = XT(c0 + t, j);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int t = 0; t <= i; ++t) sacc = fma(XT(c0 + i, c0 + t), yv[t], sacc);
+        out[i] = sacc;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) XT(c0 + i, j) = out[i];
     }
     __syncthreads();
-    // (3) trailing update, 4 x 4 micro-tiles of the lower triangle
-    const int nt = nrow >> 2;
-    for (int idx = tid; idx < nt * nt; idx += 256) {
-      const int ti = idx / nt, tj = idx - ti * nt;
-      if (tj > ti) continue;
-      const double* Pi = S + (r0 + 4 * ti) * GPC_PD_LD + c0;
-      const double* Pj = S + (r0 + 4 * tj) * GPC_PD_LD + c0;
+    // (3) rank-16 updates in 4 x 4 micro-tiles: first the trailing Cholesky tiles (lower triangle of
+    //     nt x nt), then the inverse's right-hand side Y[r][c] -= L[r][c0:c0+16] X[c0:c0+16][c], c < r0
+    const int nt = nrow >> 2, nchol = nt * nt, ncx = r0 >> 2, ntot = nchol + nt * ncx;
+    for (int idx = tid; idx < ntot; idx += 256) {
       double c[4][4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
+      if (idx < nchol) {
+        const int ti = idx / nt, tj = idx - ti * nt;
+        if (tj > ti) continue;
+        const double* Pi = S + (r0 + 4 * ti) * GPC_PD_LD + c0;
+        const double* Pj = S + (r0 + 4 * tj) * GPC_PD_LD + c0;
 #pragma unroll 4
-      for (int m = 0; m < 16; ++m) {
-        double ai[4], aj[4];
+        for (int m = 0; m < 16; ++m) {
+          double ai[4], aj[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { ai[u] = Pi[u * GPC_PD_LD + m]; aj[u] = Pj[u * GPC_PD_LD + m]; }
+          for (int u = 0; u < 4; ++u) { ai[u] = Pi[u * GPC_PD_LD + m]; aj[u] = Pj[u * GPC_PD_LD + m]; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], aj[v], c[u][v]);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], aj[v], c[u][v]);
-      }
+          for (int v = 0; v < 4; ++v) {
+            const int i = r0 + 4 * ti + u, j = r0 + 4 * tj + v;
+            if (j <= i) S[i * GPC_PD_LD + j] -= c[u][v];
+          }
+      } else {
+        const int e = idx - nchol;
+        const int ti = e / ncx, tc = e - ti * ncx;
+        const int rr = r0 + 4 * ti, cc = 4 * tc;
+        const double* Pi = S + rr * GPC_PD_LD + c0;
+#pragma unroll 4
+        for (int m = 0; m < 16; ++m) {
+          double ai[4], xv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u) ai[u] = Pi[u * GPC_PD_LD + m];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int i = r0 + 4 * ti + u, j = r0 + 4 * tj + v;
-          if (j <= i) S[i * GPC_PD_LD + j] -= c[u][v];
+          for (int v = 0; v < 4; ++v) xv[v] = (c0 + m >= cc + v) ? XT(c0 + m, cc + v) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], xv[v], c[u][v]);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) XT(rr + u, cc + v) -= c[u][v];
+      }
     }
     __syncthreads();
   }
   if (bad && tid == 0) atomicCAS(status, 0, p + 1);
-
-  // X = L^-1 block row by block row:  X_rc = -T_r (sum_{m = c}^{r-1} L_rm X_mc),  T_r = X_rr
-#pragma unroll 1
-  for (int r = 1; r < 8; ++r) {
-    for (int e = tid; e < r * 256; e += 256) {
-      const int c = e >> 8, i = (e >> 4) & 15, j = e & 15;
-      const double* Lrow = S + (16 * r + i) * GPC_PD_LD;
-      double sacc = 0.0;
-      for (int t = j; t < 16; ++t) sacc = fma(Lrow[16 * c + t], XT(16 * c + t, 16 * c + j), sacc);  // m == c: X_cc lower
-      for (int k = 16 * (c + 1); k < 16 * r; ++k) sacc = fma(Lrow[k], XT(k, 16 * c + j), sacc);
-      W[e] = sacc;
-    }
-    __syncthreads();
-    for (int e = tid; e < r * 256; e += 256) {
-      const int c = e >> 8, i = (e >> 4) & 15, j = e & 15;
-      double sacc = 0.0;
-      for (int t = 0; t <= i; ++t) sacc = fma(XT(16 * r + i, 16 * r + t), W[(c << 8) + (t << 4) + j], sacc);
-      XT(16 * r + i, 16 * c + j) = -sacc;
-    }
-    __syncthreads();
-  }
+#pragma unroll 8
   for (int e = tid; e < 128 * 128; e += 256) {
     const int r = e >> 7, c = e & 127;
     Ap[(long)r * ld + c] = (c <= r) ? S[r * GPC_PD_LD + c] : 0.0;
@@ -195,56 +223,63 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
 }
 
 // ------------------------------------------------------------------------------------------
-// Panel solve: L_ip = A_ip * X_pp^T  for i > p (TRSM expressed as a DMMA contraction with the
-// inverted diagonal block).  grid = nb - p - 1.
+// Panel solve: L_ip = A_ip * X_pp^T  for block rows i > p (TRSM expressed as a DMMA contraction
+// with the inverted diagonal block), in place.  One CTA owns 64 rows of the panel and computes
+// both 64-column halves before it stores either (its rows are read by no other CTA).
+// grid = 2 (nb - p - 1) - row0/64 ...: rows [r_lo, r_hi) in units of 64.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_trsm_panel(double* __restrict__ A,
-                                                                  const double* __restrict__ X, long ld, int p) {
+__global__ void __launch_bounds__(gpc64::NT, 4) k_trsm_panel(double* __restrict__ A, const double* __restrict__ X,
+                                                             long ld, int p, int r64_lo) {
   extern __shared__ double sm[];
-  const int i = p + 1 + blockIdx.x;
-  double acc[4][4][2];
-  gpcg::zero_acc(acc);
-  double* Aip = A + (long)i * 128 * ld + (long)p * 128;
+  const long r0 = ((long)r64_lo + blockIdx.x) * 64;
+  double* Arow = A + r0 * ld + (long)p * 128;
   const double* Xpp = X + (long)p * 128 * ld + (long)p * 128;
-  gpcg::mainloop<false>(Aip, ld, Xpp, ld, 0, 128, acc, sm);
-  gpcg::store_tile(Aip, ld, acc, 1.0, 0.0);
+  double acc0[4][4][2], acc1[4][4][2];
+  gpcg::zero_acc(acc0);
+  gpcg::zero_acc(acc1);
+  gpc64::mainloop<false>(Arow, ld, Xpp, ld, 0, 64, acc0, sm);             // X_pp lower: columns 0..63 need k < 64
+  gpc64::mainloop<false>(Arow, ld, Xpp + 64 * ld, ld, 0, 128, acc1, sm);
+  gpc64::store_tile(Arow, ld, acc0, 1.0, 0.0);
+  gpc64::store_tile(Arow + 64, ld, acc1, 1.0, 0.0);
 }
 
-// Trailing update: A_ij -= L_ip L_jp^T for p < j <= i.  grid (m, m), m = nb - p - 1.
-__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_syrk_panel(double* __restrict__ A, long ld, int p) {
+// Trailing update: A_ij -= L_ip L_jp^T over 64 x 64 tiles with row tile ti in [t_lo, t_hi) and column
+// tile tj in [c_lo, c_hi), tj <= ti (all in units of 64 rows).  grid (c_hi - c_lo, t_hi - t_lo).
+__global__ void __launch_bounds__(gpc64::NT, 4) k_syrk_panel(double* __restrict__ A, long ld, int p, int t_lo,
+                                                             int c_lo) {
   extern __shared__ double sm[];
-  const int j = p + 1 + blockIdx.x, i = p + 1 + blockIdx.y;
-  if (j > i) return;
+  const int tj = c_lo + blockIdx.x, ti = t_lo + blockIdx.y;
+  if (tj > ti) return;
   double acc[4][4][2];
   gpcg::zero_acc(acc);
-  gpcg::mainloop<false>(A + (long)i * 128 * ld + (long)p * 128, ld, A + (long)j * 128 * ld + (long)p * 128, ld, 0,
-                        128, acc, sm);
-  gpcg::store_tile(A + (long)i * 128 * ld + (long)j * 128, ld, acc, -1.0, 1.0);
+  gpc64::mainloop<false>(A + (long)ti * 64 * ld + (long)p * 128, ld, A + (long)tj * 64 * ld + (long)p * 128, ld, 0, 128,
+                         acc, sm);
+  gpc64::store_tile(A + (long)ti * 64 * ld + (long)tj * 64, ld, acc, -1.0, 1.0);
 }
 
 // ------------------------------------------------------------------------------------------
-// Triangular inverse by recursive doubling.  At level `sb` (half-size in tiles) node q covers
-// tiles [a0, a0 + 2 sb) with split mid = a0 + sb:
-//   phase 0:  T[B, A] = L[B, A] * X[A, A]          (k over A-range, >= column tile)
-//   phase 1:  X[B, A] = - X[B, B] * T[B, A]        (k over B-range, <= row tile)
-// grid (sb, sb, nodes); tiles past the matrix end exit.
+// Triangular inverse by recursive doubling.  At level `sb` (half-size in 128-blocks) node q covers
+// blocks [a0, a0 + 2 sb) with split mid = a0 + sb:
+//   phase 0:  T[B, A] = L[B, A] * X[A, A]          (k over the A-range, >= the column tile)
+//   phase 1:  X[B, A] = - X[B, B] * T[B, A]        (k over the B-range, <= the row tile)
+// grid (2 sb, 2 sb, nodes) over 64 x 64 tiles; tiles past the matrix end exit.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_linv_level(const double* __restrict__ L,
-                                                                  double* __restrict__ X,
-                                                                  double* __restrict__ T, long ld, int nb, int sb,
-                                                                  int phase) {
+__global__ void __launch_bounds__(gpc64::NT, 4) k_linv_level(const double* __restrict__ L, double* __restrict__ X,
+                                                             double* __restrict__ T, long ld, int nb, int sb,
+                                                             int phase) {
   extern __shared__ double sm[];
-  const int a0 = blockIdx.z * 2 * sb, mid = a0 + sb;
-  const int aj = a0 + blockIdx.x, bi = mid + blockIdx.y;
-  if (bi >= nb) return;
+  const int a0 = blockIdx.z * 2 * sb, mid = a0 + sb;           // in 128-blocks
+  const int aj = 2 * a0 + blockIdx.x;                          // column tile (64s) inside the A-range
+  const int bi = 2 * mid + (2 * sb - 1 - (int)blockIdx.y);     // row tile (64s) inside the B-range, long k first
+  if (bi >= 2 * nb) return;
   double acc[4][4][2];
   gpcg::zero_acc(acc);
   if (phase == 0) {
-    gpcg::mainloop<true>(L + (long)bi * 128 * ld, ld, X + (long)aj * 128, ld, aj * 128, mid * 128, acc, sm);
-    gpcg::store_tile(T + (long)bi * 128 * ld + (long)aj * 128, ld, acc, 1.0, 0.0);
+    gpc64::mainloop<true>(L + (long)bi * 64 * ld, ld, X + (long)aj * 64, ld, aj * 64, mid * 128, acc, sm);
+    gpc64::store_tile(T + (long)bi * 64 * ld + (long)aj * 64, ld, acc, 1.0, 0.0);
   } else {
-    gpcg::mainloop<true>(X + (long)bi * 128 * ld, ld, T + (long)aj * 128, ld, mid * 128, (bi + 1) * 128, acc, sm);
-    gpcg::store_tile(X + (long)bi * 128 * ld + (long)aj * 128, ld, acc, -1.0, 0.0);
+    gpc64::mainloop<true>(X + (long)bi * 64 * ld, ld, T + (long)aj * 64, ld, mid * 128, (bi + 1) * 64, acc, sm);
+    gpc64::store_tile(X + (long)bi * 64 * ld + (long)aj * 64, ld, acc, -1.0, 0.0);
   }
 }
 

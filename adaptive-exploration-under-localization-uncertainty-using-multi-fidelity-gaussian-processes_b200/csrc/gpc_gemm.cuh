@@ -154,3 +154,108 @@ __device__ __forceinline__ double rowsumsq_tile(const double (&acc)[4][4][2], do
 }
 
 }  // namespace gpcg
+
+// ------------------------------------------------------------------------------------------
+// The small-tile shape: 64 x 64 CTA tile, 4 warps of 32 x 32, BK = 16, two cp.async stages,
+// 40 KB of shared memory -> 4 CTAs per SM.  Measured 35.0 TFLOP/s against 30.2 for the shape
+// above (profiles/r01/gemm_variants_r01.txt): several small CTAs per SM cover each other's
+// barrier and pipeline-fill bubbles.  Used by the factorisation kernels; k_vt has its own copy
+// of this loop because it chains two k-segments through one pipeline.
+// ------------------------------------------------------------------------------------------
+namespace gpc64 {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 128;
+constexpr int LDT = 20, LDN = 68;
+constexpr int A_STAGE = BM * LDT;                 // 1280 doubles
+constexpr int STAGE = A_STAGE + BN * LDT;         // B slot holds 64 x 20 (k-contiguous) or 16 x 68 (n-contiguous)
+constexpr int SMEM_BYTES = 2 * STAGE * 8;         // 40960
+
+template <bool B_N>
+__device__ __forceinline__ void load_stage(double* As, double* Bs, const double* __restrict__ A, long lda,
+                                           const double* __restrict__ B, long ldb, int k0, int tid) {
+#pragma unroll
+  for (int c = tid; c < BM * (BK / 2); c += NT) {
+    const int r = c >> 3, q = c & 7;
+    cp_async16(As + r * LDT + 2 * q, A + (long)r * lda + k0 + 2 * q);
+  }
+  if (!B_N) {
+#pragma unroll
+    for (int c = tid; c < BN * (BK / 2); c += NT) {
+      const int r = c >> 3, q = c & 7;
+      cp_async16(Bs + r * LDT + 2 * q, B + (long)r * ldb + k0 + 2 * q);
+    }
+  } else {
+#pragma unroll
+    for (int c = tid; c < BK * (BN / 2); c += NT) {
+      const int kr = c >> 5, q = c & 31;
+      cp_async16(Bs + kr * LDN + 2 * q, B + (long)(k0 + kr) * ldb + 2 * q);
+    }
+  }
+}
+
+// acc += A[:, kbeg:kend] * op(B)[kbeg:kend, :]; kbeg / kend multiples of 16.  A: first row of the
+// 64-row tile (k contiguous).  B (B_N = false): first row of the 64-row tile (k contiguous);
+// B (B_N = true): column n0 of row k = 0 (rows are k).  On return the CTA is synchronised.
+template <bool B_N>
+__device__ __forceinline__ void mainloop(const double* __restrict__ A, long lda, const double* __restrict__ B,
+                                         long ldb, int kbeg, int kend, double (&acc)[4][4][2], double* smem) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1, lr = lane >> 2, lc = lane & 3;
+  const int nk = (kend - kbeg) / BK;
+  if (nk > 0) load_stage<B_N>(smem, smem + A_STAGE, A, lda, B, ldb, kbeg, tid);
+  cp_async_commit();
+  for (int it = 0; it < nk; ++it) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (it + 1 < nk) {
+      double* st = smem + ((it + 1) & 1) * STAGE;
+      load_stage<B_N>(st, st + A_STAGE, A, lda, B, ldb, kbeg + (it + 1) * BK, tid);
+    }
+    cp_async_commit();
+    const double* As = smem + (it & 1) * STAGE;
+    const double* Ap = As + (wm * 32 + lr) * LDT + lc;
+    const double* Bp = B_N ? (As + A_STAGE + lc * LDN + wn * 32 + lr) : (As + A_STAGE + (wn * 32 + lr) * LDT + lc);
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) a[f] = Ap[f * 8 * LDT + kk * 4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) b[g] = B_N ? Bp[kk * 4 * LDN + g * 8] : Bp[g * 8 * LDT + kk * 4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dmma884(acc[f][g][0], acc[f][g][1], a[f], b[g]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+__device__ __forceinline__ int acc_row(int f) { return (threadIdx.x >> 6) * 32 + f * 8 + ((threadIdx.x & 31) >> 2); }
+__device__ __forceinline__ int acc_col(int g) { return ((threadIdx.x >> 5) & 1) * 32 + g * 8 + 2 * (threadIdx.x & 3); }
+
+// C[tile] = beta * C[tile] + alpha * acc  (tile origin already applied)
+__device__ __forceinline__ void store_tile(double* __restrict__ C, long ldc, const double (&acc)[4][4][2],
+                                           double alpha, double beta) {
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const int r = acc_row(f);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double2* p = reinterpret_cast<double2*>(C + (long)r * ldc + acc_col(g));
+      double2 v;
+      if (beta != 0.0) {
+        v = *p;
+        v.x = fma(alpha, acc[f][g][0], beta * v.x);
+        v.y = fma(alpha, acc[f][g][1], beta * v.y);
+      } else {
+        v.x = alpha * acc[f][g][0];
+        v.y = alpha * acc[f][g][1];
+      }
+      *p = v;
+    }
+  }
+}
+
+}  // namespace gpc64

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_assemble_train(const __grid_constant__ 
 // replaces: scipy cho_factor (NIGP.py:43,154,288) / LAPACK dpotrf inside GPy pdinv.
 // ------------------------------------------------------------------------------------------
 #define GPC_PD_LD 129
-constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 8) * 8;
+constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 32) * 8;
 
 __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
                                                        int p, int* __restrict__ status) {
@@ -81,42 +81,53 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
   for (int kb = 0; kb < 8; ++kb) {
     const int c0 = kb * 16;
     if (warp == 0) {
-      const int l = lane & 15;  // lanes 16..31 mirror lanes 0..15 (keeps every shuffle full-warp)
-      double a[16], invd[16];
+      // (1) 16 x 16 diagonal sub-block: lane l owns row l in registers; the pivot's reciprocal
+      //     square root and the column of multipliers travel through shared memory (broadcast
+      //     reads), two __syncwarp per column -- no shuffle chains on the critical path.
+      const int l = lane & 15;  // lanes 16..31 shadow lanes 0..15
+      double* colb = S + 128 * GPC_PD_LD;  // 16 multipliers
+      double* invs = colb + 16;            // 16 reciprocal pivots
+      double a[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = (j <= l) ? S[(c0 + l) * GPC_PD_LD + c0 + j] : 0.0;
-      bool isbad = false;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        double d = __shfl_sync(0xffffffffu, a[k], k);
-        if (!(d > 0.0)) { isbad = true; d = 1.0; }
-        double inv = rsqrt(d);
-        inv = inv * fma(-0.5 * d * inv, inv, 1.5);  // one more Newton step: full double accuracy
-        const double dd = d * inv;
-        invd[k] = inv;
-        if (l == k) a[k] = dd;
-        else if (l > k) a[k] *= inv;
-#pragma unroll
-        for (int j = k + 1; j < 16; ++j) {
-          const double ljk = __shfl_sync(0xffffffffu, a[k], j);
-          if (l >= j) a[j] = fma(-a[k], ljk, a[j]);
+        if (lane == k) {
+          double d = a[k];
+          if (!(d > 0.0)) { bad = 1; d = 1.0; }
+          double inv = rsqrt(d);
+          inv = inv * fma(-0.5 * d * inv, inv, 1.5);  // one more Newton step: full double accuracy
+          invs[k] = inv;
         }
-      }
-      if (isbad && lane == 0) bad = 1;
-      // T = L_kk^-1, column l per lane, right-looking: once x_k is final every later row is updated
-      double x[16];
+        __syncwarp();
+        const double inv = invs[k];
+        if (l == k) a[k] *= inv;  // d / sqrt(d) = sqrt(d)
+        else if (l > k) {
+          a[k] *= inv;
+          if (lane < 16) colb[l] = a[k];
+        }
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        x[k] *= invd[k];
-#pragma unroll
-        for (int i = k + 1; i < 16; ++i) x[i] = fma(-__shfl_sync(0xffffffffu, a[k], i), x[k], x[i]);
+        for (int j = k + 1; j < 16; ++j)
+          if (l >= j) a[j] = fma(-a[k], colb[j], a[j]);
       }
       if (lane < 16) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j <= l) S[(c0 + l) * GPC_PD_LD + c0 + j] = a[j];
+      }
+      __syncwarp();
+      // T = L_kk^-1, column l per lane, right-looking; L is read back from shared memory (broadcast)
+      double x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        x[k] *= invs[k];
+#pragma unroll
+        for (int i = k + 1; i < 16; ++i) x[i] = fma(-S[(c0 + i) * GPC_PD_LD + c0 + k], x[k], x[i]);
+      }
+      if (lane < 16) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (i >= l) XT(c0 + i, c0 + l) = x[i];

@@ -157,14 +157,62 @@ def cpu_posterior(N, M_sample, F, params, steps=1, warmup=0, tile=20000):
     return M_sample * len(times) / sum(times), t_factor, sum(times) / len(times)
 
 
+def blas_threads():
+    """Threads the BLAS behind NumPy/SciPy actually uses (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def use_all_host_cores():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
+def cpu_nigp(X, y, noise_diag, M_sample, tile=10000):
+    from oracle import gp_oracle as go
+    ls, sf, sy = NIGP_HYP["ls"], NIGP_HYP["sigma_f"], NIGP_HYP["sigma_y"]
+    t0 = time.perf_counter()
+    K = go.SE_ARD_kernel(X, X, ls, sf)
+    f = go.Factor(K + np.diag(sy ** 2 + noise_diag), y)
+    t_factor = time.perf_counter() - t0
+    rng = np.random.default_rng(5)
+    Xs = rng.uniform([0, 0, 0], [10, 20, 10], (M_sample, 3))
+    t0 = time.perf_counter()
+    for o in range(0, M_sample, tile):
+        Kxs = go.SE_ARD_kernel(Xs[o:o + tile], X, ls, sf)
+        mean = Kxs @ f.alpha
+        tmp = f.half_solve(Kxs.T)
+        var = np.maximum(sf - np.sum(tmp * tmp, 0) + 1e-12, 1e-12)
+    dt = time.perf_counter() - t0
+    return M_sample / dt, t_factor
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_cores()
     N, F = args.n_train, 2
     M_sample = min(args.m_test, int(2e4 * 8192 / N) // 2)
-    pts_s, t_factor, t_step = cpu_posterior(N, M_sample, F, MF2_PARAMS, steps=args.steps, warmup=args.warmup)
-    cores = os.cpu_count()
+    if args.workload == "nigp":
+        X4, y = make_train(N, 3)
+        nd = np.full(N, 0.01)
+        ts = []
+        for it in range(args.warmup + args.steps):
+            p, t_factor = cpu_nigp(X4[:, :3], y, nd, M_sample)
+            if it >= args.warmup:
+                ts.append(M_sample / p)
+        pts_s, t_step = M_sample * len(ts) / sum(ts), sum(ts) / len(ts)
+    else:
+        pts_s, t_factor, t_step = cpu_posterior(N, M_sample, F, MF2_PARAMS, steps=args.steps, warmup=args.warmup)
+    cores = blas_threads()
     line = {"impl": "reference", "metric": METRIC, "value": pts_s, "unit": "pts/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -177,7 +225,29 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+NIGP_HYP = dict(ls=np.array([2.0, 3.0, 2.5]), sigma_f=4.0, sigma_y=0.2, sigma_x=np.array([0.1, 0.1, 0.05]))
+
+
+def apply_workload_defaults(args):
+    """--workload mf2  = BASELINE configs[1] (the headline line);
+       --workload nigp = BASELINE configs[2]: NIGP noisy-input GP, N = 8192, 2^21 test points per GPU
+                         (16 M sharded over 8), per-point training noise from the posterior-mean gradients."""
+    if args.workload == "nigp":
+        args.n_train = args.n_train or 8192
+        args.m_test = args.m_test or (1 << 21)
+    else:
+        args.n_train = args.n_train or 2048
+        args.m_test = args.m_test or 1000000
+
+
 def workload_config(args):
+    if args.workload == "nigp":
+        return {"workload": "configs[2]: NIGP noisy-input SE-ARD GP (sigma_x-derived per-point noise), N=%d train, "
+                            "%d test points per GPU (a 16M-point set sharded over 8 GPUs), posterior mean + variance "
+                            "(NIGP.predict semantics), fixed hypers" % (args.n_train, args.m_test),
+                "n_train": args.n_train, "m_test_per_gpu": args.m_test, "fidelities": 1, "chunk_rows": args.chunk,
+                "l2": "inputs larger than L2: each launch streams a %d MB K* chunk (> 126 MB L2)"
+                      % (args.chunk * args.n_train * 8 // 2 ** 20)}
     return {"workload": "configs[1]: synthetic 2-fidelity AR1 (Kennedy-O'Hagan) GP, N=%d train, %d-point 3D test grid "
                         "at the top fidelity per GPU, posterior mean + noise-inclusive variance, fixed hypers"
                         % (args.n_train, args.m_test),
@@ -212,8 +282,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gpcore.build()
 
-    N, M, F = args.n_train, args.m_test, 2
-    X4, y = make_train(N, F)
+    nigp_mode = args.workload == "nigp"
+    N, M, F = args.n_train, args.m_test, (1 if nigp_mode else 2)
+    X4, y = make_train(N, F if F > 1 else 3)
+    if nigp_mode:
+        X4[:, 3] = 0.0
     n = int(round(M ** (1.0 / 3)))
     if n ** 3 == M:
         # every rank owns a different 1 M-point grid (shifted by a sub-cell offset) -> weak scaling
@@ -222,10 +295,22 @@ def run_ours(args):
         Xs4_host = np.hstack([np.random.default_rng(100 + rank).uniform([0, 0, 0], [10, 20, 10], (M, 3)),
                               np.full((M, 1), F - 1.0)])
 
-    core = gpcore.GPCore(L.KIND_MF_AR1_RBF, F, local)
-    core.set_chunk(args.chunk)
-    core.set_hypers(MF2_PARAMS, 1e-8)
-    core.set_data(X4, y)
+    noise_diag = None
+    if nigp_mode:
+        # per-point input-noise variance v_i = sum_d (d mean / d x_d)^2 sigma_x_d^2 (NIGP.py:222,251-252)
+        from gpcore import nigp as gnigp
+        _, g = gnigp.compute_post_mean_and_gradients(X4[:, :3], y, NIGP_HYP["ls"], NIGP_HYP["sigma_f"],
+                                                     NIGP_HYP["sigma_y"], device=local)
+        noise_diag = np.sum(g ** 2 * NIGP_HYP["sigma_x"][None, :] ** 2, axis=1)
+        core = gpcore.GPCore(L.KIND_NIGP, 1, local)
+        core.set_chunk(args.chunk)
+        core.set_hypers(np.concatenate([NIGP_HYP["ls"], [NIGP_HYP["sigma_f"], NIGP_HYP["sigma_y"]]]), 0.0)
+        core.set_data(X4, y, noise_diag)
+    else:
+        core = gpcore.GPCore(L.KIND_MF_AR1_RBF, F, local)
+        core.set_chunk(args.chunk)
+        core.set_hypers(MF2_PARAMS, 1e-8)
+        core.set_data(X4, y)
     t0 = time.perf_counter()
     if world > 1:
         from gpcore.sharding import broadcast_factor
@@ -245,7 +330,7 @@ def run_ours(args):
     dmean = torch.empty(M, dtype=torch.float64, device="cuda")
     dvar = torch.empty(M, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    flags = L.INCLUDE_NOISE | L.CLIP_DIAG
+    flags = L.NIGP_FLOOR if nigp_mode else (L.INCLUDE_NOISE | L.CLIP_DIAG)
 
     def step_dev():
         core.predict_dev(dXs.data_ptr(), M, dmean.data_ptr(), dvar.data_ptr(), flags)
@@ -291,17 +376,35 @@ def run_ours(args):
     value = world * M * args.steps / (ms * 1e-3)
 
     # ---- e2e: reference-facing API, host buffers (pinned), copies inside the timed region ---------
-    kern = LinearMultiFidelityKernel([RBF(3, ARD=True), RBF(3, ARD=True)])
-    model = GPyLinearMultiFidelityModel(X4, y[:, None], kern, n_fidelities=F, device=local)
-    model.param_array[:] = MF2_PARAMS
-    wrap = GPyMultiOutputWrapper(model, F, n_optimization_restarts=1)
-    model._ensure_factor().set_chunk(args.chunk)
-    pinned = torch.from_numpy(Xs4_host).pin_memory()
-    Xs_pinned = pinned.numpy()
     out = {}
+    if nigp_mode:
+        from gpcore.nigp import NIGP
+        wrap = NIGP(verbose=False, device=local)
+        wrap.lengthscales_, wrap.sigma_f_, wrap.sigma_y_ = NIGP_HYP["ls"], NIGP_HYP["sigma_f"], NIGP_HYP["sigma_y"]
+        wrap.sigma_x_, wrap.X_train_, wrap.y_train_, wrap.noise_diag_train_ = NIGP_HYP["sigma_x"], X4[:, :3], y, noise_diag
+        wrap._factor().set_chunk(args.chunk)
+        pinned = torch.from_numpy(np.ascontiguousarray(Xs4_host[:, :3])).pin_memory()
+        Xs_pinned = pinned.numpy()
+        api = "gpcore.nigp.NIGP.predict(Xs) -> gpc_predict (host pointers)"
+        h2d = M * 32
+
+        def predict_api(Xq):
+            mu, var = wrap.predict(Xq)
+            return mu[:, None], var[:, None]
+    else:
+        kern = LinearMultiFidelityKernel([RBF(3, ARD=True), RBF(3, ARD=True)])
+        model = GPyLinearMultiFidelityModel(X4, y[:, None], kern, n_fidelities=F, device=local)
+        model.param_array[:] = MF2_PARAMS
+        wrap = GPyMultiOutputWrapper(model, F, n_optimization_restarts=1)
+        model._ensure_factor().set_chunk(args.chunk)
+        pinned = torch.from_numpy(Xs4_host).pin_memory()
+        Xs_pinned = pinned.numpy()
+        api = "gpcore.emukit GPyMultiOutputWrapper.predict(X4) -> gpc_predict (host pointers, pinned)"
+        h2d = M * 32
+        predict_api = wrap.predict
 
     def step_e2e():
-        mu, var = wrap.predict(Xs_pinned)
+        mu, var = predict_api(Xs_pinned)
         out["chk"] = float(mu[0, 0]) + float(var[-1, 0])
 
     for _ in range(args.warmup):
@@ -318,7 +421,7 @@ def run_ours(args):
         dt = float(t[0])
     e2e = world * M * args.steps / dt
     # parity spot check of the e2e result against the device-resident result
-    mu, var = wrap.predict(Xs_pinned[:4096])
+    mu, var = predict_api(Xs_pinned[:4096])
     dm, dv = dmean[:4096].cpu().numpy(), dvar[:4096].cpu().numpy()
     err_m, err_v = float(np.max(np.abs(mu[:, 0] - dm))), float(np.max(np.abs(var[:, 0] - dv)))
     if not (err_m <= 1e-9 * max(1.0, float(np.max(np.abs(dm)))) and err_v <= 1e-9 * MF2_PARAMS[0]):
@@ -351,21 +454,28 @@ def run_ours(args):
                 "share_of_step": hot_ms / ms}
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------
-    M_cpu = min(M, int(2e4 * 8192 / N) // 2)
-    cpu_pts, cpu_factor, _ = cpu_posterior(N, M_cpu, F, MF2_PARAMS, steps=1, warmup=0)
-    cpu = {"value": cpu_pts, "unit": "pts/s", "cores": os.cpu_count(), "kind": "port",
-           "sample": "%d test points (tile of the %d-point workload), N=%d; factor %.2f s outside the sample; "
-                     "NumPy/SciPy restatement of the GPy/emukit arithmetic" % (M_cpu, M, N, cpu_factor)}
+    cpu = None
+    if world == 1:
+        M_cpu = min(M, int(2e4 * 8192 / N) // 2)
+        if nigp_mode:
+            cpu_pts, cpu_factor = cpu_nigp(X4[:, :3], y, noise_diag, M_cpu)
+            what = "the oracle restatement of NIGP.predict (diagonal only; the reference builds the M x M matrix)"
+        else:
+            cpu_pts, cpu_factor, _ = cpu_posterior(N, M_cpu, F, MF2_PARAMS, steps=1, warmup=0)
+            what = "NumPy/SciPy restatement of the GPy/emukit arithmetic"
+        cpu = {"value": cpu_pts, "unit": "pts/s", "cores": blas_threads(), "kind": "port",
+               "sample": "%d test points (tile of the %d-point workload), N=%d; factor %.2f s outside the sample; %s"
+                         % (M_cpu, M, N, cpu_factor, what)}
 
     line = {"metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-            "e2e": {"value": e2e, "unit": "pts/s", "h2d_bytes_per_step": int(M * 32), "d2h_bytes_per_step": int(M * 16),
-                    "api": "gpcore.emukit GPyMultiOutputWrapper.predict(X4) -> gpc_predict (host pointers, pinned)"},
+            "e2e": {"value": e2e, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(M * 16),
+                    "api": api},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast}
 
-    if args.ig:
+    if args.ig and not nigp_mode:
         line["ig"] = bench_ig(args, gpcore, L, torch, local)
     print(json.dumps(line))
     if dist is not None:
@@ -411,12 +521,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-train", type=int, default=2048)
-    ap.add_argument("--m-test", type=int, default=1000000)
+    ap.add_argument("--workload", default="mf2", choices=["mf2", "nigp"])
+    ap.add_argument("--n-train", type=int, default=0)
+    ap.add_argument("--m-test", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--ig", type=int, default=1)
     ap.add_argument("--ig-candidates", type=int, default=65536)
     args = ap.parse_args()
+    apply_workload_defaults(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -442,12 +442,19 @@ def run_ours(args):
                    "MEASURED_PEAKS.json has no FP64 entry"
     except Exception:
         pass
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same config only)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "k_vt_traffic.json")))
+        if tr["n_train"] == N and tr["chunk_rows"] == args.chunk and not nigp_mode:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     rows_per_launch = M * args.steps / max(hot_n, 1)
     alg_flops_per_launch = rows_per_launch * float(N) * float(N)
     avg_ms = hot_ms / max(hot_n, 1)
     achieved = alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "k_vt<false,true> (V = L^-1 K*, FP64 DMMA, fused sum of squares)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches": hot_n, "avg_launch_ms": avg_ms,
                 "algorithmic_flops_per_launch": alg_flops_per_launch,
                 "executed_flops_per_launch": hot_flops / max(hot_n, 1),

@@ -12,6 +12,7 @@
 #include "gpc_factor.cuh"
 #include "gpc_grad.cuh"
 #include "gpc_ig.cuh"
+#include "gpc_ozaki.cuh"
 #include "gpc_predict.cuh"
 
 #define GPC_VERSION 100
@@ -63,6 +64,11 @@ struct gpc_handle_s {
   bool have_extra = false;
   // prediction workspaces
   DevBuf Xs4, Kx, meanpart, sumsq, gradpart, mean, var, Vt, cov, grads, ediag;
+  // tcgen05 / INT8 path (gpc_ozaki.cuh): digit images of L^-1 and of the current K* chunk
+  DevBuf Bimg, sBv, Aimg;
+  bool have_slices = false;
+  int mode = GPC_MODE_INT8;
+  int n_sm = 0;
   // information-gain workspaces
   DevBuf gX4, gVt, gS, gSinv, gT, Bt, Zt, cand_off, cand_I, cand_aux, cand_rows, cand_mask, gram, gramZ;
   // hot-kernel timing
@@ -114,6 +120,9 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_ig_logdet_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_ig_selfgrid_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
+  CK(cudaFuncSetAttribute(k_vt_i8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device));
   return GPC_OK;
 }
 
@@ -265,23 +274,96 @@ int launch_vt(gpc_handle h, long m_pad) {
   return launch_vt_on<STORE_V, SUMSQ>(h, h->Kx.d(), h->X.d(), h->n_pad, m_pad, h->Vt.d(), h->sumsq.d());
 }
 
+// INT8 digits of the rows of L^-1 (built lazily once per factorisation) and the K* scale.
+int ensure_slices(gpc_handle h) {
+  if (h->have_slices) return GPC_OK;
+  const long np = h->n_pad;
+  CK(h->Bimg.ensure((size_t)np * np * gpoz::S));
+  CK(h->sBv.ensure((size_t)np * 8));
+  k_slice_rows<<<(unsigned)(np / 8), 256, 0, h->stream>>>(h->X.d(), np, np, static_cast<int8_t*>(h->Bimg.p), h->sBv.d());
+  CKL();
+  h->have_slices = true;
+  return GPC_OK;
+}
+
+double kstar_scale(gpc_handle h) {
+  double kmax = 0.0;
+  for (int i = 0; i < h->F; ++i) kmax = std::fmax(kmax, h->hyp.kdiag[i]);  // |k(a, b)| <= max prior variance
+  int e = 0;
+  std::frexp(kmax, &e);
+  return std::ldexp(1.0, e + 2);  // |k| / sA < 1/4
+}
+
+// V = K* X^T on the INT8 tensor cores for one chunk whose digit image is in h->Aimg.
+template <bool STORE_V, bool SUMSQ>
+int launch_vt_i8(gpc_handle h, long m_pad, double* Vt, double* sumsq) {
+  const long np = h->n_pad;
+  const int nb2 = (int)(np / gpoz::TN);
+  const int n_items = (int)(m_pad / gpoz::TM) * ((nb2 + 1) / 2);
+  const int grid = n_items < h->n_sm ? n_items : h->n_sm;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->hot_timing) {
+    if (h->ev_used + 2 > h->ev.size()) {
+      for (int i = 0; i < 64; ++i) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->ev.push_back(e);
+      }
+    }
+    e0 = h->ev[h->ev_used++];
+    e1 = h->ev[h->ev_used++];
+    CK(cudaEventRecord(e0, h->stream));
+  }
+  k_vt_i8<STORE_V, SUMSQ><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(
+      static_cast<const int8_t*>(h->Aimg.p), static_cast<const int8_t*>(h->Bimg.p), h->sBv.d(), kstar_scale(h), np, nb2,
+      m_pad, n_items, Vt, sumsq);
+  CKL();
+  if (h->hot_timing) {
+    CK(cudaEventRecord(e1, h->stream));
+    h->hot_flops += (double)m_pad * (double)np * (double)(np + 64);  // FP64-equivalent; x 21 digit GEMMs in int8 ops
+  }
+  return GPC_OK;
+}
+
 // One chunk of the posterior (device pointers; M <= m_chunk).  d_sx != NULL adds the NIGP
 // test-input-noise term (needs the mean gradients, so the gradient variant of k_kstar runs).
 int predict_chunk(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags,
                   const double* d_sx = nullptr, long sx_rows = 0) {
   const long m_pad = round_up(M, 128);
+  const long np = h->n_pad;
   int rc;
-  if ((rc = ensure_pred_ws(h, m_pad, false, d_sx != nullptr))) return rc;
   const bool want_var = dvar && !(flags & GPC_MEAN_ONLY);
-  if (want_var) {
-    if (d_sx) rc = launch_kstar<true, true>(h, dXs4, M, m_pad);
-    else rc = launch_kstar<false, true>(h, dXs4, M, m_pad);
-    if (rc) return rc;
-    if ((rc = launch_vt<false, true>(h, m_pad))) return rc;
+  int nchunks = (int)((np + KS_COLS - 1) / KS_COLS);
+  if (want_var && h->mode == GPC_MODE_INT8 && np <= gpoz::MAX_K) {
+    // tcgen05 path: K* goes straight to int8 digit images, the contraction runs on the INT8 tensor cores
+    nchunks = (int)((np + KI_COLS - 1) / KI_COLS);
+    if ((rc = ensure_slices(h))) return rc;
+    CK(h->Aimg.ensure((size_t)m_pad * np * gpoz::S));
+    CK(h->meanpart.ensure((size_t)nchunks * m_pad * 8));
+    CK(h->sumsq.ensure((size_t)(2 * h->nb) * m_pad * 8));
+    if (d_sx) CK(h->gradpart.ensure((size_t)nchunks * 3 * m_pad * 8));
+    const dim3 grid((unsigned)(m_pad / 128), (unsigned)nchunks);
+    if (d_sx)
+      k_kstar_i8<true><<<grid, 128, 0, h->stream>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, dXs4, M, m_pad,
+                                                    kstar_scale(h), static_cast<int8_t*>(h->Aimg.p), h->meanpart.d(),
+                                                    h->gradpart.d());
+    else
+      k_kstar_i8<false><<<grid, 128, 0, h->stream>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, dXs4, M, m_pad,
+                                                     kstar_scale(h), static_cast<int8_t*>(h->Aimg.p), h->meanpart.d(),
+                                                     nullptr);
+    CKL();
+    if ((rc = launch_vt_i8<false, true>(h, m_pad, nullptr, h->sumsq.d()))) return rc;
   } else {
-    if ((rc = launch_kstar<false, false>(h, dXs4, M, m_pad))) return rc;
+    if ((rc = ensure_pred_ws(h, m_pad, false, d_sx != nullptr))) return rc;
+    if (want_var) {
+      if (d_sx) rc = launch_kstar<true, true>(h, dXs4, M, m_pad);
+      else rc = launch_kstar<false, true>(h, dXs4, M, m_pad);
+      if (rc) return rc;
+      if ((rc = launch_vt<false, true>(h, m_pad))) return rc;
+    } else {
+      if ((rc = launch_kstar<false, false>(h, dXs4, M, m_pad))) return rc;
+    }
   }
-  const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
   k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(
       h->hyp, dXs4, M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), 2 * h->nb, h->gradpart.d(),
       want_var ? d_sx : nullptr, sx_rows, dmean, want_var ? dvar : nullptr, flags);
@@ -347,7 +429,7 @@ int gpc_destroy(gpc_handle h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
                     &h->status, &h->Wm, &h->gpart, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
-                    &h->cov, &h->grads, &h->ediag, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
+                    &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -503,6 +585,7 @@ int gpc_factor(gpc_handle h, double* nlml, double* logdet) {
   h->logdet = sc[0];
   h->nlml = 0.5 * sc[1] + 0.5 * sc[0] + 0.5 * (double)h->N * log(2.0 * M_PI);
   h->factored = true;
+  h->have_slices = false;
   if (nlml) *nlml = h->nlml;
   if (logdet) *logdet = h->logdet;
   return GPC_OK;
@@ -636,6 +719,7 @@ int gpc_adopt_factor(gpc_handle h, double logdet) {
     return fail(h, GPC_ERR_STATE, "gpc_adopt_factor needs hypers, data and gpc_factor_state_dev buffers");
   h->logdet = logdet;
   h->factored = true;
+  h->have_slices = false;
   return GPC_OK;
 }
 
@@ -854,6 +938,15 @@ int gpc_spd_stats(gpc_handle h, const double* cov, long M, const double* e, doub
 
 void* gpc_stream(gpc_handle h) { return h ? (void*)h->stream : nullptr; }
 long gpc_launch_count(gpc_handle h) { return h ? h->launches : 0; }
+
+int gpc_set_mode(gpc_handle h, int mode) {
+  if (!h) return GPC_ERR_ARG;
+  if (mode != GPC_MODE_FP64 && mode != GPC_MODE_INT8) return fail(h, GPC_ERR_ARG, "unknown mode");
+  h->mode = mode;
+  return GPC_OK;
+}
+
+int gpc_get_mode(gpc_handle h) { return h ? h->mode : -1; }
 
 int gpc_set_chunk(gpc_handle h, long m_chunk) {
   if (!h) return GPC_ERR_ARG;

@@ -5,12 +5,14 @@
 // do.  This file evaluates the SAME contraction V = K* X^T exactly-enough on the INT8 tensor cores
 // (4.56 POP/s measured, profiles/r01/umma_i8_rate_r01.txt) with the Ozaki splitting scheme:
 //
-//   x = scale * 2^-49 * v,  v = rint(x / scale * 2^49) = sum_{p<S} d_p 128^(S-1-p),  d_p in [-64, 63]
-//   (balanced base-128 digits, S = 7 int8 "slices" per operand), so that
-//   sum_k a_k b_k = sA sB 2^-98 sum_{p,q} 128^(12-p-q) sum_k d^A_pk d^B_qk.
-// Every digit GEMM C_pq = D^A_p (D^B_q)^T is exact in int32 (|d| <= 64, K <= 65536); the pairs with
-// p + q = t share one TMEM accumulator; pairs with p + q >= S (below 2^-49 of the operand scales)
-// are dropped.  S (S + 1) / 2 = 28 digit GEMMs replace one FP64 GEMM.
+//   x = scale * 2^-48 * v,  v = rint(x / scale * 2^48) = sum_{p<S} d_p 256^(S-1-p),  d_p in [-128, 127]
+//   (balanced base-256 digits, S = 6 int8 "slices" per operand; with |x| / scale < 1/4 the bytes of
+//   v + 0x808080808080 are the digits + 128, so slicing is one add and byte permutes), so that
+//   sum_k a_k b_k = sA sB 2^-96 sum_{p,q} 256^(10-p-q) sum_k d^A_pk d^B_qk.
+// Every digit GEMM C_pq = D^A_p (D^B_q)^T is exact in int32 (|d| <= 128, up to 6 pairs per
+// accumulator: K <= 21845); the pairs with p + q = t share one TMEM accumulator; pairs with
+// p + q >= S (below 2^-48 of the operand scales) are dropped.  S (S + 1) / 2 = 21 digit GEMMs replace
+// one FP64 GEMM.
 //
 // Operand images.  Digits are stored in global memory already in the shared-memory image the MMA
 // consumes (K-major, no swizzle, 8 x 16-byte core matrices): a (rows x 64-byte) k-block of one
@@ -20,8 +22,8 @@
 //   B image  [n_pad/64 ][n_pad/64][S][4 KB]   rows of X x train index (digits of X_i,: / sB_i)
 //
 // Kernel k_vt_i8: persistent, one CTA per SM, 192 threads:
-//   warp 0   TMA producer (one lane): 2-stage ring of (A k-block, B k-block) = 84 KB per stage
-//   warp 1   MMA issuer (one lane): 56 tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) per stage into
+//   warp 0   TMA producer (one lane): 3-stage ring of (A k-block, B k-block) = 72 KB per stage
+//   warp 1   MMA issuer (one lane): 42 tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) per stage into
 //            S accumulators of 64 TMEM columns; tcgen05.commit frees the stage / publishes the tile
 //   warps 2-5 epilogue: tcgen05.ld the S int32 levels, recombine in int64, scale to FP64 and either
 //            reduce sum_i V(n, i)^2 per test row (one thread owns a row: no shuffles) or store V.
@@ -31,14 +33,17 @@
 
 namespace gpoz {
 
-constexpr int S = 7;                 // int8 slices per operand
+constexpr int S = 6;                 // int8 slices (base-256 digits) per operand
 constexpr int BK = 64;               // k-block (bytes = k values)
 constexpr int TM = 128, TN = 64;     // MMA tile: 128 test rows x 64 train rows
 constexpr int A_SLICE = TM * BK;     // 8192 B
 constexpr int B_SLICE = TN * BK;     // 4096 B
 constexpr int A_STAGE = S * A_SLICE, B_STAGE = S * B_SLICE;
-constexpr int STAGE_BYTES = A_STAGE + B_STAGE;   // 86016
-constexpr int STAGES = 2;
+constexpr int STAGE_BYTES = A_STAGE + B_STAGE;   // 73728
+constexpr int STAGES = 3;
+constexpr int MAX_K = 16384;         // int32 accumulators: 6 pairs x K x 128^2 < 2^31
+constexpr double DIGIT_MUL = 281474976710656.0;           // 2^48
+constexpr long long DIGIT_BIAS = 0x808080808080LL;        // 128 (256^6 - 1) / 255
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 constexpr int NT = 192;
 constexpr uint32_t TMEM_COLS = 512;
@@ -83,14 +88,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
       : "r"(taddr));
 }
 
-// Balanced base-128 digits of v (|v| < 2^47, i.e. |x| / scale < 1/4): d[S-1] least significant.
-__device__ __forceinline__ void digits7(long long v, int (&d)[S]) {
+// The S digit bytes of 16 consecutive values for slice p, packed as one 16-byte vector: u[] holds
+// v + DIGIT_BIAS (bytes = digits + 128, byte 0 least significant = slice S-1).
+__device__ __forceinline__ uint4 pack_slice(const unsigned long long (&u)[16], int p) {
+  const int b = S - 1 - p;  // byte index inside the 48-bit value
+  uint32_t w[4];
 #pragma unroll
-  for (int p = S - 1; p >= 0; --p) {
-    const int low = (int)(((v + 64) & 127) - 64);
-    d[p] = low;
-    v = (v - low) >> 7;
+  for (int q = 0; q < 4; ++q) {
+    uint32_t x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long v = u[4 * q + e];
+      const uint32_t word = b < 4 ? (uint32_t)v : (uint32_t)(v >> 32);
+      x[e] = (word >> (8 * (b & 3))) & 255u;
+    }
+    w[q] = (x[0] | (x[1] << 8) | (x[2] << 16) | (x[3] << 24)) ^ 0x80808080u;  // digit = byte - 128
   }
+  return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 }  // namespace gpoz
@@ -114,30 +128,146 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   frexp(mx, &e);  // mx = f 2^e, f in [0.5, 1)  ->  |x| / 2^(e+2) < 1/4: the top balanced digit cannot overflow
   const double scale = (mx > 0.0) ? ldexp(1.0, e + 2) : 1.0;
   if (lane == 0) sB[i] = scale;
-  const double mul = 562949953421312.0 / scale;  // 2^49 / scale
+  const double mul = DIGIT_MUL / scale;
   const long jb = i >> 6, r = i & 63;
   const long nkb = n_pad >> 6;
   // every 16-byte chunk (16 consecutive k) of every slice; k-blocks beyond the diagonal stay zero
   for (long c = lane; c < (jb + 1) * 4; c += 32) {
     const long kb = c >> 2, cc = c & 3;
-    int dg[16][S];
+    unsigned long long uu[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const long k = kb * 64 + cc * 16 + u;
       const double x = (k <= i) ? row[k] : 0.0;
-      digits7(__double2ll_rn(x * mul), dg[u]);
+      uu[u] = (unsigned long long)(__double2ll_rn(x * mul) + DIGIT_BIAS);
     }
     int8_t* base = Bimg + ((jb * nkb + kb) * S) * (long)B_SLICE + (r >> 3) * 512 + cc * 128 + (r & 7) * 16;
 #pragma unroll
-    for (int p = 0; p < S; ++p) {
-      uint32_t w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        w[q] = (uint32_t)(dg[4 * q][p] & 255) | ((uint32_t)(dg[4 * q + 1][p] & 255) << 8) |
-               ((uint32_t)(dg[4 * q + 2][p] & 255) << 16) | ((uint32_t)(dg[4 * q + 3][p] & 255) << 24);
-      *reinterpret_cast<uint4*>(base + (long)p * B_SLICE) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(base + (long)p * B_SLICE) = pack_slice(uu, p);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K* assembly straight into the A digit image (+ posterior mean, + optional mean gradients): the
+// FP64 cross-covariance never goes to HBM -- 7 bytes per element are written instead of 8.
+// CTA = 128 threads = the 128 test rows of one MMA tile, one row per thread; the CTA covers 256
+// train columns (four 64-wide k-blocks) staged by 1-D TMA bulk copies.  All lanes of a warp work
+// on the SAME train column at a time (shared-memory reads are broadcasts, the fidelity of the
+// column is warp-uniform), and 16 consecutive columns of a row become one 16-byte store per slice
+// -- eight lanes fill a 128-byte core matrix.  The mean needs no cross-lane reduction.
+//   k = sum_{m <= min(fi, fj)} w_i[m] coef[fj][m] base_m(x - x'),  w_i[m] = coef[fi][m] var[m]
+// grid (m_pad / 128, n_pad / 256).   meanpart [n_pad/256][m_pad], gradpart [n_pad/256][3][m_pad].
+// ------------------------------------------------------------------------------------------
+constexpr int KI_COLS = 256;
+
+template <bool WITH_GRAD>
+__global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp h, const double* __restrict__ Xt,
+                                                  const double* __restrict__ alpha, long N, long n_pad,
+                                                  const double* __restrict__ Xs4, long M, long m_pad, double sA,
+                                                  int8_t* __restrict__ Aimg, double* __restrict__ meanpart,
+                                                  double* __restrict__ gradpart) {
+  using namespace gpoz;
+  __shared__ __align__(128) double tr[5][KI_COLS];
+  __shared__ double hil[GPC_MAXF][4];
+  __shared__ double hcoef[GPC_MAXF][GPC_MAXF];
+  __shared__ double wS[GPC_MAXF][128];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int mt = blockIdx.x;
+  const long j0 = (long)blockIdx.y * KI_COLS;
+  const long nkb = n_pad >> 6;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int ncol = (int)((n_pad - j0) < KI_COLS ? (n_pad - j0) : KI_COLS);  // multiple of 128
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)ncol * 8u;
+    mbar_expect_tx(&bar, 5u * bytes);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tma_bulk_g2s(&tr[c][0], Xt + (long)c * n_pad + j0, bytes, &bar);
+    tma_bulk_g2s(&tr[4][0], alpha + j0, bytes, &bar);
+  }
+  if (tid < GPC_MAXF * 3) hil[tid / 3][tid % 3] = h.inv_l[tid / 3][tid % 3] * (h.base == 0 ? 0.70710678118654752440 : 1.0);
+  if (tid < GPC_MAXF * GPC_MAXF) hcoef[tid >> 2][tid & 3] = h.coef[tid >> 2][tid & 3];
+  const long n = (long)mt * TM + tid;
+  double ax = 0, ay = 0, az = 0, af = -1.0;
+  if (n < M) { ax = Xs4[n * 4]; ay = Xs4[n * 4 + 1]; az = Xs4[n * 4 + 2]; af = Xs4[n * 4 + 3]; }
+  const bool live = n < M && af >= 0.0;
+  const int fi = gpc_fid(h, af);
+  const int F = h.F, base = h.base;
+#pragma unroll
+  for (int m = 0; m < GPC_MAXF; ++m) wS[m][tid] = (live && m <= fi && m < F) ? h.coef[fi][m] * h.var[m] : 0.0;
+  const int fimax = __reduce_max_sync(0xffffffffu, live ? fi : 0);
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  // fidelity of every staged column as an int, in place (low word of the double slot)
+  int* fi32 = reinterpret_cast<int*>(&tr[3][0]);
+  for (int j = tid; j < ncol; j += 128) {
+    const int f = gpc_fid(h, tr[3][j]);
+    fi32[2 * j] = (j0 + j < N) ? f : -1;  // -1: padding column, every coefficient is zero
+  }
+  __syncthreads();
+  const double mul = DIGIT_MUL / sA;
+  double mu = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+  const int r = tid;
+#pragma unroll 1
+  for (int ch = 0; ch < (ncol >> 4); ++ch) {  // 16-column chunks: ch >> 2 = k-block inside the CTA, ch & 3 = chunk
+    // the AR1 sum runs over m <= min(max test fidelity in the warp, max train fidelity in the chunk);
+    // coef[fj][m] is zero for m > fj, w[m] is zero for m > fi, so over-running a term adds exact zeros
+    int fjmax = 0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) fjmax = max(fjmax, fi32[2 * (ch * 16 + u)]);
+    const int mmc = fjmax < fimax ? fjmax : fimax;
+    double k[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) k[u] = 0.0;
+#pragma unroll 1
+    for (int m = 0; m <= mmc; ++m) {
+      const double c0 = hil[m][0], c1 = hil[m][1], c2 = hil[m][2], wm = wS[m][tid];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int j = ch * 16 + u;
+        const double sx = (tr[0][j] - ax) * c0, sy = (tr[1][j] - ay) * c1, sz = (tr[2][j] - az) * c2;
+        const double q = fma(sx, sx, fma(sy, sy, sz * sz));
+        double e;
+        if (base == 0) {
+          e = exp(-q);
+        } else {
+          const double rt = 1.7320508075688772 * sqrt(q);
+          e = (1.0 + rt) * exp(-rt);
+        }
+        const int fj = fi32[2 * j];
+        k[u] = fma(wm * (fj >= 0 ? hcoef[fj][m] : 0.0), e, k[u]);
+      }
+    }
+    unsigned long long v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = ch * 16 + u;
+      const double ka = k[u] * tr[4][j];
+      mu += ka;
+      if (WITH_GRAD) {
+        g0 = fma(ka, tr[0][j] - ax, g0);
+        g1 = fma(ka, tr[1][j] - ay, g1);
+        g2 = fma(ka, tr[2][j] - az, g2);
+      }
+      v[u] = (unsigned long long)(__double2ll_rn(k[u] * mul) + DIGIT_BIAS);
+    }
+    const long kb = (j0 >> 6) + (ch >> 2);
+    int8_t* dst = Aimg + (((long)mt * nkb + kb) * S) * (long)A_SLICE + (r >> 3) * 512 + (ch & 3) * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long)p * A_SLICE) = pack_slice(v, p);
+  }
+  meanpart[(long)blockIdx.y * m_pad + n] = mu;
+  if (WITH_GRAD) {
+    double* gp = gradpart + (long)blockIdx.y * 3 * m_pad;
+    gp[n] = g0 * h.inv_l[0][0] * h.inv_l[0][0];
+    gp[m_pad + n] = g1 * h.inv_l[0][1] * h.inv_l[0][1];
+    gp[2 * m_pad + n] = g2 * h.inv_l[0][2] * h.inv_l[0][2];
+  }
+  (void)lane;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,8 +316,8 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
         for (int sg = 0; sg < nseg; ++sg) {
           const int jb = jbs[sg];
           for (int kb = 0; kb <= jb; ++kb, ++it) {
-            const int st = it & 1;
-            if (it >= STAGES) mbar_wait_guarded(&empty_bar[st], ((it >> 1) - 1) & 1);
+            const int st = it % STAGES;
+            if (it >= STAGES) mbar_wait_guarded(&empty_bar[st], ((it / STAGES) - 1) & 1);
             uint8_t* dst = smem + st * STAGE_BYTES;
             mbar_expect_tx(&full_bar[st], STAGE_BYTES);
             tma_bulk_g2s(dst, Aimg + (((long)mt * nkb_total + kb) * S) * (long)A_SLICE, A_STAGE, &full_bar[st]);
@@ -212,8 +342,8 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
           if (tile > 0) mbar_wait_guarded(&tmem_empty_bar, (tile - 1) & 1);  // epilogue drained the accumulators
           asm volatile("tcgen05.fence::after_thread_sync;");
           for (int kb = 0; kb <= jb; ++kb, ++it) {
-            const int st = it & 1;
-            mbar_wait_guarded(&full_bar[st], (it >> 1) & 1);
+            const int st = it % STAGES;
+            mbar_wait_guarded(&full_bar[st], (it / STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t sa = smem_u32(smem + st * STAGE_BYTES), sb = sa + A_STAGE;
 #pragma unroll
@@ -260,34 +390,34 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
             for (int j = 0; j < 16; ++j) hi[j] = v[j];
           }
 #pragma unroll
-          for (int t = 1; t < 4; ++t) {
+          for (int t = 1; t < 3; ++t) {
             int32_t v[16];
             tmem_ld16(lane_addr + t * TN + c0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 128 + v[j];
+            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 256 + v[j];
           }
           {
             int32_t v[16];
-            tmem_ld16(lane_addr + 4 * TN + c0, v);
+            tmem_ld16(lane_addr + 3 * TN + c0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 16; ++j) lo[j] = v[j];
           }
 #pragma unroll
-          for (int t = 5; t < S; ++t) {
+          for (int t = 4; t < S; ++t) {
             int32_t v[16];
             tmem_ld16(lane_addr + t * TN + c0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 128 + v[j];
+            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 256 + v[j];
           }
-          // comb = sum_t C_t 128^(6-t) = hi 128^3 + lo ;  V = comb 2^-56 sA sB[i]
+          // comb = sum_t C_t 256^(5-t) = hi 256^3 + lo ;  V = comb 2^-96 256^5 sA sB[i] = comb 2^-56 sA sB[i]
           const double* sb = sB + (long)jb * TN + c0;
           double vv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const double comb = fma((double)hi[j], 2097152.0, (double)lo[j]);
+            const double comb = fma((double)hi[j], 16777216.0, (double)lo[j]);
             vv[j] = comb * (COMB_SCALE * sA) * sb[j];
             ss = fma(vv[j], vv[j], ss);
           }

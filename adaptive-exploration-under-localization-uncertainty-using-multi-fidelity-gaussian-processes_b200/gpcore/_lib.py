@@ -19,6 +19,7 @@ GPC_OK, GPC_ERR_NOT_PD, GPC_ERR_SHAPE, GPC_ERR_CUDA, GPC_ERR_STATE, GPC_ERR_ARG 
 KIND_SF_RBF, KIND_SF_MAT32, KIND_MF_AR1_RBF, KIND_MF_AR1_MAT32, KIND_NIGP = range(5)
 INCLUDE_NOISE, CLIP_DIAG, CLIP_COV, NIGP_FLOOR, MEAN_ONLY = 1, 2, 4, 8, 16
 IG_FIRST_PREADDED = 1
+MODE_FP64, MODE_INT8 = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -85,6 +86,8 @@ SIGNATURES = {
     "gpc_spd_stats": (C.c_int, [_h, _dp, C.c_long, _dp, _dp, _dp, _dp]),
     "gpc_stream": (C.c_void_p, [_h]),
     "gpc_launch_count": (C.c_long, [_h]),
+    "gpc_set_mode": (C.c_int, [_h, C.c_int]),
+    "gpc_get_mode": (C.c_int, [_h]),
     "gpc_set_chunk": (C.c_int, [_h, C.c_long]),
     "gpc_hot_kernel_time": (C.c_int, [_h, _dp, _lp, _dp, C.c_int]),
     "gpc_enable_hot_timing": (C.c_int, [_h, C.c_int]),

@@ -217,6 +217,13 @@ class GPCore:
     def launch_count(self):
         return int(self.lib.gpc_launch_count(self.h))
 
+    def set_mode(self, mode):
+        """``_lib.MODE_INT8`` (default: tcgen05 INT8 Ozaki contraction) or ``_lib.MODE_FP64`` (DMMA)."""
+        self._ck(self.lib.gpc_set_mode(self.h, int(mode)))
+
+    def mode(self):
+        return int(self.lib.gpc_get_mode(self.h))
+
     def set_chunk(self, m):
         self._ck(self.lib.gpc_set_chunk(self.h, int(m)))
 

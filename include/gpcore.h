@@ -54,6 +54,16 @@ enum gpc_kind {
 #define GPC_NIGP_FLOOR 8u    /* NIGP.py:327-333: var = max(var + 1e-12, 1e-12); cov += 1e-12 I    */
 #define GPC_MEAN_ONLY 16u    /* skip the variance (var may be NULL)                               */
 
+/* gpc_set_mode: how the posterior variance contraction V = L^-1 K* runs
+ *   GPC_MODE_FP64  FP64 DMMA (mma.sync.m8n8k4.f64), bounded by the 37 TFLOP/s FP64 pipe of sm_100a
+ *   GPC_MODE_INT8  (default) Ozaki splitting on the tcgen05 INT8 tensor cores: both operands are cut
+ *                  into 6 balanced base-256 digits, the 21 digit GEMMs are exact in int32 (TMEM), their
+ *                  recombination carries 2^-48 of the operand scales -- results agree with the FP64 path
+ *                  to ~1e-12 relative, far inside the 1e-9 parity tolerance (tests/test_gpu_int8.py).
+ *                  Used for N <= 16384 (int32 accumulator range); larger problems run in FP64. */
+#define GPC_MODE_FP64 0
+#define GPC_MODE_INT8 1
+
 /* gpc_ig_seq flags */
 #define GPC_IG_FIRST_PREADDED 1u /* GraceRIGV3.py:454-455: point 0 is appended before it is predicted */
 
@@ -166,6 +176,8 @@ int gpc_spd_stats(gpc_handle h, const double* cov, long M, const double* e, doub
 void* gpc_stream(gpc_handle h);                 /* cudaStream_t all kernels are launched on     */
 long gpc_launch_count(gpc_handle h);            /* kernels launched by this handle so far        */
 int gpc_set_chunk(gpc_handle h, long m_chunk);  /* test points per launch batch (default 16384)  */
+int gpc_set_mode(gpc_handle h, int mode);       /* GPC_MODE_FP64 | GPC_MODE_INT8                   */
+int gpc_get_mode(gpc_handle h);
 /* Device time of the dominant kernel (the L^-1 K* DMMA contraction) accumulated with CUDA events
  * on gpc_stream() since the last reset, the number of its launches and the floating-point
  * operations those launches executed (2 x multiply-adds over the padded triangular k-range). */

@@ -1,0 +1,111 @@
+"""GPU parity of the tcgen05 / INT8 (Ozaki splitting) variance path against the FP64 DMMA path and
+the oracle.  Same tolerance as everywhere: 1e-9 relative, normwise (max|d| <= 1e-9 max(|ref|, var))."""
+import numpy as np
+import pytest
+
+from conftest import golden, normwise
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+MF_PARAMS = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+SF_PARAMS = np.array([4.0, 2.0, 3.0, 2.5, 0.05])
+
+
+@pytest.fixture(scope="module")
+def gpcore_mod(built_lib):
+    import gpcore
+    return gpcore
+
+
+@pytest.fixture(scope="module")
+def go():
+    from oracle import gp_oracle
+    return gp_oracle
+
+
+def synth(rng, N, F):
+    X = rng.uniform([0, 0, 0], [10, 20, 10], (N, 3))
+    f = rng.integers(0, F, (N, 1)).astype(float) if F > 1 else np.zeros((N, 1))
+    y = np.sin(X[:, 0]) * np.cos(0.3 * X[:, 1]) + 0.2 * f[:, 0] + 0.05 * rng.standard_normal(N)
+    return np.hstack([X, f]), y
+
+
+@pytest.mark.parametrize("N,F,M", [(1, 1, 5), (100, 1, 333), (129, 3, 1000), (300, 1, 128), (709, 3, 2000),
+                                     (1000, 2, 4097), (2048, 2, 20000)])
+def test_int8_matches_fp64_and_oracle(gpcore_mod, go, N, F, M):
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(1000 + N)
+    X4, y = synth(rng, N, F)
+    if F == 1:
+        kind, p = L_.KIND_SF_RBF, SF_PARAMS
+    elif F == 3:
+        kind, p = L_.KIND_MF_AR1_RBF, MF_PARAMS
+    else:
+        kind, p = L_.KIND_MF_AR1_RBF, np.array([4.0, 2.0, 3.0, 2.5, 1.0, 1.5, 2.0, 2.0, 0.8, 0.05, 0.02])
+    core = gpcore_mod.GPCore(kind, F, 0)
+    core.set_hypers(p, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    Xs4 = np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (M, 3)), rng.integers(0, F, (M, 1)).astype(float)])
+    Xs4[: min(M, N) // 2, :3] = X4[: min(M, N) // 2, :3] + 1e-3      # next to training points: var << prior (cancellation)
+    flags = L_.INCLUDE_NOISE | L_.CLIP_DIAG
+    core.set_mode(L_.MODE_FP64)
+    m0, v0 = core.predict(Xs4, flags)
+    core.set_mode(L_.MODE_INT8)
+    m1, v1 = core.predict(Xs4, flags)
+    scale = float(np.max(core.kernel_matrix(Xs4[:1], Xs4[:1]))) if F == 1 else 4.64
+    assert normwise(m1, m0) < 1e-12
+    assert normwise(v1, v0, scale) < 1e-10, normwise(v1, v0, scale)
+    if N <= 1000:
+        ref = go.SFGP(X4[:, :3], y, p, gram=False) if F == 1 else go.MFGP(X4, y, p, F=F, gram=False)
+        mu, var = ref.predict(Xs4[:, :3] if F == 1 else Xs4)
+        assert normwise(m1, mu[:, 0]) < TOL and normwise(v1, var[:, 0], scale) < TOL
+    core.set_chunk(256)
+    m2, v2 = core.predict(Xs4, flags)
+    assert np.array_equal(m1, m2) and np.array_equal(v1, v2)        # independent of the launch chunking
+    core.close()
+
+
+def test_int8_matern_and_nigp_noisy_inputs(gpcore_mod, go):
+    from gpcore.nigp import NIGP
+    L_ = gpcore_mod._lib
+    g, d = golden("nigp_field.npz"), golden("field_data.npz")
+    sf = float(g["sigma_f"])
+    m = NIGP(verbose=False)
+    m.lengthscales_, m.sigma_f_, m.sigma_y_, m.sigma_x_ = g["ls"], sf, float(g["sigma_y"]), g["sigma_x"]
+    m.X_train_, m.y_train_, m.noise_diag_train_ = d["Xh"], d["y"], g["noise_diag"]
+    assert m._factor().mode() == L_.MODE_INT8                       # the default
+    mean, var = m.predict(d["test"])
+    assert normwise(mean, g["mean"]) < TOL and normwise(var, g["var"], sf) < TOL       # reference NIGP.py values
+    _, var_in = m.predict(d["test"], Xs_input_noise=g["sigma_x"])
+    assert normwise(var_in, g["var_in"], sf) < TOL
+    rng = np.random.default_rng(77)
+    X4, y = synth(rng, 500, 1)
+    core = gpcore_mod.GPCore(L_.KIND_SF_MAT32, 1, 0)
+    core.set_hypers(SF_PARAMS, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    Xs4 = np.hstack([rng.uniform(0, 10, (900, 3)), np.zeros((900, 1))])
+    mu, var = go.SFGP(X4[:, :3], y, SF_PARAMS, kind=go.KIND_MAT32, gram=False).predict(Xs4[:, :3])
+    m1, v1 = core.predict(Xs4, L_.INCLUDE_NOISE | L_.CLIP_DIAG)
+    assert normwise(m1, mu[:, 0]) < TOL and normwise(v1, var[:, 0], 4.0) < TOL
+    core.close()
+
+
+def test_int8_extreme_scales(gpcore_mod, go):
+    """Large and tiny kernel variances / noise: the fixed-point scales follow the hypers and the rows of L^-1."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(5)
+    X4, y = synth(rng, 400, 1)
+    Xs4 = np.hstack([rng.uniform(0, 10, (700, 3)), np.zeros((700, 1))])
+    for p in (np.array([2500.0, 2.0, 3.0, 2.5, 1e-4]), np.array([1e-3, 1.0, 1.0, 1.0, 1e-6]), np.array([4.0, 0.3, 0.3, 0.3, 2.0])):
+        core = gpcore_mod.GPCore(L_.KIND_SF_RBF, 1, 0)
+        core.set_hypers(p, 1e-8)
+        core.set_data(X4, y * np.sqrt(p[0]))
+        core.factor()
+        ref = go.SFGP(X4[:, :3], y * np.sqrt(p[0]), p, gram=False)
+        mu, var = ref.predict(Xs4[:, :3])
+        m1, v1 = core.predict(Xs4, L_.INCLUDE_NOISE | L_.CLIP_DIAG)
+        assert normwise(m1, mu[:, 0]) < 1e-8 and normwise(v1, var[:, 0], p[0]) < TOL, p
+        core.close()

@@ -218,7 +218,9 @@ def test_sfgp_predict_field(gpcore_mod, go, kind):
     assert np.allclose(cov, cov.T, rtol=0, atol=0)
     # the diagonal of the full covariance is the marginal variance (before the 1e-15 clip)
     _, var_sub = gp.predict(d["test_sub"])
-    assert normwise(np.diag(cov), var_sub[:, 0], 4.0) < 1e-12
+    # (the diagonal path runs on the INT8 tensor cores by default, the full covariance in FP64 DMMA:
+    #  they agree to the ~1e-11 the 7-digit splitting carries, two orders inside the parity tolerance)
+    assert normwise(np.diag(cov), var_sub[:, 0], 4.0) < 1e-10
     # noise-free latent prediction
     _, lat = gp.predict(d["test_sub"], include_likelihood=False)
     assert normwise(lat + SF_PARAMS[-1], var_sub, 4.0) < 1e-12
@@ -309,7 +311,7 @@ def test_mfgp_two_fidelity_rho_and_matern(gpcore_mod, go):
         mu0, var0 = ref.predict(Xs4)
         assert normwise(mean, mu0[:, 0]) < TOL and normwise(var, var0[:, 0], 4.0) < TOL
         mo, _ = core.predict(Xs4, 0, want_var=False)
-        assert np.array_equal(mo, mean)
+        assert normwise(mo, mean) < 1e-13     # mean-only and mean+var assemble K* in different kernels
         core.close()
 
 
@@ -576,11 +578,17 @@ def test_hot_kernel_timing_hooks(gpcore_mod):
     core.set_hypers(SF_PARAMS, 1e-8)
     core.set_data(X4, y)
     core.factor()
-    n0 = core.launch_count()
+    Xq = np.hstack([rng.uniform(0, 10, (4096, 3)), np.zeros((4096, 1))])
     core.enable_hot_timing(True)
-    core.predict(np.hstack([rng.uniform(0, 10, (4096, 3)), np.zeros((4096, 1))]), 0)
-    ms, n, fl = core.hot_kernel_time(reset=True)
-    assert n == 1 and ms > 0 and fl == 4096 * 512 * (512 + 32)
-    assert core.launch_count() - n0 == 3               # k_kstar, k_vt, k_finalize_pred
+    for mode, flops in ((L_.MODE_FP64, 4096 * 512 * (512 + 32)), (L_.MODE_INT8, 4096 * 512 * (512 + 64))):
+        core.set_mode(mode)
+        assert core.mode() == mode
+        core.predict(Xq, 0)                             # first call of a mode may build its operand images
+        core.hot_kernel_time(reset=True)
+        n0 = core.launch_count()
+        core.predict(Xq, 0)
+        ms, n, fl = core.hot_kernel_time(reset=True)
+        assert n == 1 and ms > 0 and fl == flops
+        assert core.launch_count() - n0 == 3           # K* assembly, L^-1 K* contraction, finalize
     assert core.stream() is not None
     core.close()

@@ -65,7 +65,8 @@ struct gpc_handle_s {
   // prediction workspaces
   DevBuf Xs4, Kx, meanpart, sumsq, gradpart, mean, var, Vt, cov, grads, ediag;
   // tcgen05 / INT8 path (gpc_ozaki.cuh): digit images of L^-1 and of the current K* chunk
-  DevBuf Bimg, sBv, Aimg;
+  DevBuf Bimg, sBv, Aimg, Aimg2, meanpart2, gradpart2;
+  cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_v[2] = {nullptr, nullptr};
   bool have_slices = false;
   int mode = GPC_MODE_INT8;
   int n_sm = 0;
@@ -296,7 +297,7 @@ double kstar_scale(gpc_handle h) {
 
 // V = K* X^T on the INT8 tensor cores for one chunk whose digit image is in h->Aimg.
 template <bool STORE_V, bool SUMSQ>
-int launch_vt_i8(gpc_handle h, long m_pad, double* Vt, double* sumsq) {
+int launch_vt_i8(gpc_handle h, const int8_t* Aimg, long m_pad, double* Vt, double* sumsq) {
   const long np = h->n_pad;
   const int nb2 = (int)(np / gpoz::TN);
   const int n_items = (int)(m_pad / gpoz::TM) * ((nb2 + 1) / 2);
@@ -315,7 +316,7 @@ int launch_vt_i8(gpc_handle h, long m_pad, double* Vt, double* sumsq) {
     CK(cudaEventRecord(e0, h->stream));
   }
   k_vt_i8<STORE_V, SUMSQ><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(
-      static_cast<const int8_t*>(h->Aimg.p), static_cast<const int8_t*>(h->Bimg.p), h->sBv.d(), kstar_scale(h), np, nb2,
+      Aimg, static_cast<const int8_t*>(h->Bimg.p), h->sBv.d(), kstar_scale(h), np, nb2,
       m_pad, n_items, Vt, sumsq);
   CKL();
   if (h->hot_timing) {
@@ -325,49 +326,98 @@ int launch_vt_i8(gpc_handle h, long m_pad, double* Vt, double* sumsq) {
   return GPC_OK;
 }
 
-// One chunk of the posterior (device pointers; M <= m_chunk).  d_sx != NULL adds the NIGP
-// test-input-noise term (needs the mean gradients, so the gradient variant of k_kstar runs).
+// Posterior mean + variance of M device-resident test rows on the tcgen05 path, software-pipelined
+// over m_chunk-row chunks on two streams: the K* digit assembly of chunk i+1 (FP64 / integer
+// pipes, side stream) runs while the INT8 tensor cores contract chunk i (main stream).  The two
+// kernels need different resources, so they share the SMs: k_vt_i8 holds one CTA per SM, the
+// assembly CTAs fill the registers and shared memory that are left.
+int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags,
+                        const double* d_sx, long sx_rows) {
+  const long np = h->n_pad, mc = h->m_chunk;
+  const long mp_max = round_up(M < mc ? M : mc, 128);
+  const int nchunks = (int)((np + KI_COLS - 1) / KI_COLS);
+  int rc;
+  if ((rc = ensure_slices(h))) return rc;
+  DevBuf* Ab[2] = {&h->Aimg, &h->Aimg2};
+  DevBuf* Mb[2] = {&h->meanpart, &h->meanpart2};
+  DevBuf* Gb[2] = {&h->gradpart, &h->gradpart2};
+  const int nbuf = (M > mc) ? 2 : 1;
+  for (int b = 0; b < nbuf; ++b) {
+    CK(Ab[b]->ensure((size_t)mp_max * np * gpoz::S));
+    CK(Mb[b]->ensure((size_t)nchunks * mp_max * 8));
+    if (d_sx) CK(Gb[b]->ensure((size_t)nchunks * 3 * mp_max * 8));
+  }
+  CK(h->sumsq.ensure((size_t)(2 * h->nb) * mp_max * 8));
+  cudaStream_t s1 = h->stream, s2 = h->side;
+  CK(cudaEventRecord(h->ev_main, s1));       // the side stream starts after everything queued so far
+  CK(cudaStreamWaitEvent(s2, h->ev_main, 0));
+  const double sA = kstar_scale(h);
+  long i = 0;
+  for (long o = 0; o < M; o += mc, ++i) {
+    const long m = (M - o) < mc ? (M - o) : mc;
+    const long m_pad = round_up(m, 128);
+    const int b = (int)(i & 1);
+    const double* xs = dXs4 + o * 4;
+    if (i >= 2) CK(cudaStreamWaitEvent(s2, h->ev_v[b], 0));  // chunk i-2 no longer reads this buffer
+    const dim3 grid((unsigned)(m_pad / 128), (unsigned)nchunks);
+    if (d_sx)
+      k_kstar_i8<true><<<grid, 128, 0, s2>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, xs, m, m_pad, sA,
+                                             static_cast<int8_t*>(Ab[b]->p), Mb[b]->d(), Gb[b]->d());
+    else
+      k_kstar_i8<false><<<grid, 128, 0, s2>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, xs, m, m_pad, sA,
+                                              static_cast<int8_t*>(Ab[b]->p), Mb[b]->d(), nullptr);
+    CKL();
+    CK(cudaEventRecord(h->ev_k[b], s2));
+    CK(cudaStreamWaitEvent(s1, h->ev_k[b], 0));
+    if ((rc = launch_vt_i8<false, true>(h, static_cast<const int8_t*>(Ab[b]->p), m_pad, nullptr, h->sumsq.d()))) return rc;
+    k_finalize_pred<<<(unsigned)((m + 255) / 256), 256, 0, s1>>>(
+        h->hyp, xs, m, m_pad, Mb[b]->d(), nchunks, h->sumsq.d(), 2 * h->nb, Gb[b]->d(),
+        d_sx ? d_sx + (sx_rows == 1 ? 0 : o * 3) : nullptr, sx_rows, dmean ? dmean + o : nullptr, dvar + o, flags);
+    CKL();
+    CK(cudaEventRecord(h->ev_v[b], s1));
+  }
+  return GPC_OK;
+}
+
+inline bool use_i8(gpc_handle h, const double* dvar, unsigned flags) {
+  return dvar && !(flags & GPC_MEAN_ONLY) && h->mode == GPC_MODE_INT8 && h->n_pad <= gpoz::MAX_K;
+}
+
+// One chunk of the posterior on the FP64 path (device pointers; M <= m_chunk).  d_sx != NULL adds
+// the NIGP test-input-noise term (needs the mean gradients: the gradient variant of k_kstar runs).
 int predict_chunk(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags,
                   const double* d_sx = nullptr, long sx_rows = 0) {
   const long m_pad = round_up(M, 128);
-  const long np = h->n_pad;
   int rc;
   const bool want_var = dvar && !(flags & GPC_MEAN_ONLY);
-  int nchunks = (int)((np + KS_COLS - 1) / KS_COLS);
-  if (want_var && h->mode == GPC_MODE_INT8 && np <= gpoz::MAX_K) {
-    // tcgen05 path: K* goes straight to int8 digit images, the contraction runs on the INT8 tensor cores
-    nchunks = (int)((np + KI_COLS - 1) / KI_COLS);
-    if ((rc = ensure_slices(h))) return rc;
-    CK(h->Aimg.ensure((size_t)m_pad * np * gpoz::S));
-    CK(h->meanpart.ensure((size_t)nchunks * m_pad * 8));
-    CK(h->sumsq.ensure((size_t)(2 * h->nb) * m_pad * 8));
-    if (d_sx) CK(h->gradpart.ensure((size_t)nchunks * 3 * m_pad * 8));
-    const dim3 grid((unsigned)(m_pad / 128), (unsigned)nchunks);
-    if (d_sx)
-      k_kstar_i8<true><<<grid, 128, 0, h->stream>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, dXs4, M, m_pad,
-                                                    kstar_scale(h), static_cast<int8_t*>(h->Aimg.p), h->meanpart.d(),
-                                                    h->gradpart.d());
-    else
-      k_kstar_i8<false><<<grid, 128, 0, h->stream>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, dXs4, M, m_pad,
-                                                     kstar_scale(h), static_cast<int8_t*>(h->Aimg.p), h->meanpart.d(),
-                                                     nullptr);
-    CKL();
-    if ((rc = launch_vt_i8<false, true>(h, m_pad, nullptr, h->sumsq.d()))) return rc;
+  const int nchunks = (int)((h->n_pad + KS_COLS - 1) / KS_COLS);
+  if ((rc = ensure_pred_ws(h, m_pad, false, d_sx != nullptr))) return rc;
+  if (want_var) {
+    if (d_sx) rc = launch_kstar<true, true>(h, dXs4, M, m_pad);
+    else rc = launch_kstar<false, true>(h, dXs4, M, m_pad);
+    if (rc) return rc;
+    if ((rc = launch_vt<false, true>(h, m_pad))) return rc;
   } else {
-    if ((rc = ensure_pred_ws(h, m_pad, false, d_sx != nullptr))) return rc;
-    if (want_var) {
-      if (d_sx) rc = launch_kstar<true, true>(h, dXs4, M, m_pad);
-      else rc = launch_kstar<false, true>(h, dXs4, M, m_pad);
-      if (rc) return rc;
-      if ((rc = launch_vt<false, true>(h, m_pad))) return rc;
-    } else {
-      if ((rc = launch_kstar<false, false>(h, dXs4, M, m_pad))) return rc;
-    }
+    if ((rc = launch_kstar<false, false>(h, dXs4, M, m_pad))) return rc;
   }
   k_finalize_pred<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(
       h->hyp, dXs4, M, m_pad, h->meanpart.d(), nchunks, h->sumsq.d(), 2 * h->nb, h->gradpart.d(),
       want_var ? d_sx : nullptr, sx_rows, dmean, want_var ? dvar : nullptr, flags);
   CKL();
+  return GPC_OK;
+}
+
+// All chunks of a device-resident test set.
+int predict_rows(gpc_handle h, const double* dXs4, long M, double* dmean, double* dvar, unsigned flags,
+                 const double* d_sx, long sx_rows) {
+  if (use_i8(h, dvar, flags)) return predict_i8_pipeline(h, dXs4, M, dmean, dvar, flags, d_sx, sx_rows);
+  int rc;
+  for (long o = 0; o < M; o += h->m_chunk) {
+    const long m = (M - o) < h->m_chunk ? (M - o) : h->m_chunk;
+    if ((rc = predict_chunk(h, dXs4 + o * 4, m, dmean ? dmean + o : nullptr, dvar ? dvar + o : nullptr, flags,
+                            d_sx ? d_sx + (sx_rows == 1 ? 0 : o * 3) : nullptr, sx_rows)))
+      return rc;
+  }
   return GPC_OK;
 }
 
@@ -407,6 +457,10 @@ int gpc_create(int kind, int F, int device, gpc_handle* out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_v[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     std::string m = cudaGetErrorString(e);
     delete h;
@@ -429,10 +483,14 @@ int gpc_destroy(gpc_handle h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
                     &h->status, &h->Wm, &h->gpart, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
-                    &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
+                    &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->Aimg2, &h->meanpart2, &h->gradpart2, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+    if (h->ev_v[i]) cudaEventDestroy(h->ev_v[i]);
+  }
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
   if (h->side) cudaStreamDestroy(h->side);
@@ -752,13 +810,9 @@ int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, dou
   int rc = require_factor(h);
   if (rc) return rc;
   if (M < 0 || !dXs4) return fail(h, GPC_ERR_SHAPE, "bad test set");
+  if (M == 0) return GPC_OK;
   CK(cudaSetDevice(h->device));
-  for (long o = 0; o < M; o += h->m_chunk) {
-    const long m = (M - o) < h->m_chunk ? (M - o) : h->m_chunk;
-    if ((rc = predict_chunk(h, dXs4 + o * 4, m, dmean ? dmean + o : nullptr, dvar ? dvar + o : nullptr, flags)))
-      return rc;
-  }
-  return GPC_OK;
+  return predict_rows(h, dXs4, M, dmean, dvar, flags, nullptr, 0);
 }
 
 // Host-pointer posterior: the test rows are copied to the device in "super-chunks" of up to
@@ -791,13 +845,9 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
     CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + s0 * 4, (size_t)ms * 32, cudaMemcpyHostToDevice, h->stream));
     if (sx && sx_rows != 1)
       CK(cudaMemcpyAsync(h->ediag.p, sx + s0 * 3, (size_t)ms * 24, cudaMemcpyHostToDevice, h->stream));
-    for (long o = 0; o < ms; o += mc) {
-      const long m = (ms - o) < mc ? (ms - o) : mc;
-      if ((rc = predict_chunk(h, h->Xs4.d() + o * 4, m, mean ? h->mean.d() + o : nullptr,
-                              want_var ? h->var.d() + o : nullptr, flags,
-                              sx ? h->ediag.d() + (sx_rows == 1 ? 0 : o * 3) : nullptr, sx_rows)))
-        return rc;
-    }
+    if ((rc = predict_rows(h, h->Xs4.d(), ms, mean ? h->mean.d() : nullptr, want_var ? h->var.d() : nullptr, flags,
+                           sx ? h->ediag.d() : nullptr, sx_rows)))
+      return rc;
     if (mean) CK(cudaMemcpyAsync(mean + s0, h->mean.p, (size_t)ms * 8, cudaMemcpyDeviceToHost, h->stream));
     if (want_var) CK(cudaMemcpyAsync(var + s0, h->var.p, (size_t)ms * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

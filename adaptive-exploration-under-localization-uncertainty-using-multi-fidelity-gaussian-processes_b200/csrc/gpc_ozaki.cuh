@@ -23,7 +23,7 @@
 //
 // Kernel k_vt_i8: persistent, one CTA per SM, 192 threads:
 //   warp 0   TMA producer (one lane): 3-stage ring of (A k-block, B k-block) = 72 KB per stage
-//   warp 1   MMA issuer (one lane): 42 tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) per stage into
+//   warp 1   MMA issuer (one lane): 16 tcgen05.mma.kind::i8 (M = 128, N = 64..256, K = 32) per stage into
 //            S accumulators of 64 TMEM columns; tcgen05.commit frees the stage / publishes the tile
 //   warps 2-5 epilogue: tcgen05.ld the S int32 levels, recombine in int64, scale to FP64 and either
 //            reduce sum_i V(n, i)^2 per test row (one thread owns a row: no shuffles) or store V.
@@ -105,6 +105,24 @@ __device__ __forceinline__ uint4 pack_slice(const unsigned long long (&u)[16], i
     w[q] = (x[0] | (x[1] << 8) | (x[2] << 16) | (x[3] << 24)) ^ 0x80808080u;  // digit = byte - 128
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 8-value variant: half of a 16-byte chunk.
+__device__ __forceinline__ uint2 pack_slice8(const unsigned long long (&u)[8], int p) {
+  const int b = S - 1 - p;
+  uint32_t w[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long v = u[4 * q + e];
+      const uint32_t word = b < 4 ? (uint32_t)v : (uint32_t)(v >> 32);
+      x[e] = (word >> (8 * (b & 3))) & 255u;
+    }
+    w[q] = (x[0] | (x[1] << 8) | (x[2] << 16) | (x[3] << 24)) ^ 0x80808080u;
+  }
+  return make_uint2(w[0], w[1]);
 }
 
 }  // namespace gpoz
@@ -213,22 +231,22 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
   double mu = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
   const int r = tid;
 #pragma unroll 1
-  for (int ch = 0; ch < (ncol >> 4); ++ch) {  // 16-column chunks: ch >> 2 = k-block inside the CTA, ch & 3 = chunk
-    // the AR1 sum runs over m <= min(max test fidelity in the warp, max train fidelity in the chunk);
+  for (int c8 = 0; c8 < (ncol >> 3); ++c8) {  // 8 columns at a time = half of a 16-byte chunk of every slice
+    // the AR1 sum runs over m <= min(max test fidelity in the warp, max train fidelity of the 8 columns);
     // coef[fj][m] is zero for m > fj, w[m] is zero for m > fi, so over-running a term adds exact zeros
     int fjmax = 0;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) fjmax = max(fjmax, fi32[2 * (ch * 16 + u)]);
+    for (int u = 0; u < 8; ++u) fjmax = max(fjmax, fi32[2 * (c8 * 8 + u)]);
     const int mmc = fjmax < fimax ? fjmax : fimax;
-    double k[16];
+    double k[8];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) k[u] = 0.0;
+    for (int u = 0; u < 8; ++u) k[u] = 0.0;
 #pragma unroll 1
     for (int m = 0; m <= mmc; ++m) {
       const double c0 = hil[m][0], c1 = hil[m][1], c2 = hil[m][2], wm = wS[m][tid];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int j = ch * 16 + u;
+      for (int u = 0; u < 8; ++u) {
+        const int j = c8 * 8 + u;
         const double sx = (tr[0][j] - ax) * c0, sy = (tr[1][j] - ay) * c1, sz = (tr[2][j] - az) * c2;
         const double q = fma(sx, sx, fma(sy, sy, sz * sz));
         double e;
@@ -242,10 +260,10 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
         k[u] = fma(wm * (fj >= 0 ? hcoef[fj][m] : 0.0), e, k[u]);
       }
     }
-    unsigned long long v[16];
+    unsigned long long v[8];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int j = ch * 16 + u;
+    for (int u = 0; u < 8; ++u) {
+      const int j = c8 * 8 + u;
       const double ka = k[u] * tr[4][j];
       mu += ka;
       if (WITH_GRAD) {
@@ -255,10 +273,11 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
       }
       v[u] = (unsigned long long)(__double2ll_rn(k[u] * mul) + DIGIT_BIAS);
     }
-    const long kb = (j0 >> 6) + (ch >> 2);
-    int8_t* dst = Aimg + (((long)mt * nkb + kb) * S) * (long)A_SLICE + (r >> 3) * 512 + (ch & 3) * 128 + (r & 7) * 16;
+    const long kb = (j0 >> 6) + (c8 >> 3);
+    int8_t* dst = Aimg + (((long)mt * nkb + kb) * S) * (long)A_SLICE + (r >> 3) * 512 + ((c8 >> 1) & 3) * 128 +
+                  (r & 7) * 16 + (c8 & 1) * 8;
 #pragma unroll
-    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long)p * A_SLICE) = pack_slice(v, p);
+    for (int p = 0; p < S; ++p) *reinterpret_cast<uint2*>(dst + (long)p * A_SLICE) = pack_slice8(v, p);
   }
   meanpart[(long)blockIdx.y * m_pad + n] = mu;
   if (WITH_GRAD) {
@@ -330,7 +349,7 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
     // ===== MMA issuer =====
     if (lane == 0) {
       // c = S32 (2) @4, a = b = INT8 (1) @7 / @10, K-major, N >> 3 @17, M >> 4 @24
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);
       uint32_t it = 0, tile = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = item / npair, p = item - mt * npair;
@@ -346,15 +365,23 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
             mbar_wait_guarded(&full_bar[st], (it / STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t sa = smem_u32(smem + st * STAGE_BYTES), sb = sa + A_STAGE;
+            // Digit pair (pp, qq) accumulates into TMEM region t = pp + qq (64 columns each).  The B
+            // slices of a stage are contiguous 64-row blocks with the same row-group stride, so ONE MMA
+            // of width 64 n covers the pairs (pp, q0 .. q0 + n - 1) and lands in regions t0 .. t0 + n - 1:
+            // 8 wide MMAs per k-step instead of 21 narrow ones -- the A digits are fetched from shared
+            // memory 8 times instead of 21 (shared-memory bandwidth is what bounds this kernel).
 #pragma unroll
-            for (int t = 0; t < S; ++t) {
+            for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-              for (int pp = 0; pp <= t; ++pp) {
-                const int qq = t - pp;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk)
-                  umma_i8(tmem_base + t * TN, umma_desc(sa + pp * A_SLICE + kk * 256),
-                          umma_desc(sb + qq * B_SLICE + kk * 256), idesc, (kb > 0 || pp > 0 || kk > 0) ? 1u : 0u);
+              for (int pp = 0; pp < S; ++pp) {
+                int q0 = 0;
+                while (q0 < S - pp) {
+                  const int nsl = (S - pp - q0) > 4 ? 4 : (S - pp - q0);  // slices in this MMA (N <= 256)
+                  const uint32_t idesc = idesc0 | ((uint32_t)((nsl * TN) >> 3) << 17);
+                  umma_i8(tmem_base + (pp + q0) * TN, umma_desc(sa + pp * A_SLICE + kk * 256),
+                          umma_desc(sb + q0 * B_SLICE + kk * 256), idesc, (kb > 0 || kk > 0 || pp > 0) ? 1u : 0u);
+                  q0 += nsl;
+                }
               }
             }
             umma_commit(&empty_bar[st]);  // the stage may be refilled once these MMAs have read it

@@ -241,6 +241,14 @@ def apply_workload_defaults(args):
 
 
 def workload_config(args):
+    cfg = _workload_config(args)
+    cfg["variance_path"] = ("int8: Ozaki splitting, 6 base-256 digits per operand, 21 exact digit GEMMs on the tcgen05 INT8 "
+                            "tensor cores, FP64 results to ~1e-12 (parity tolerance 1e-9)") if args.mode == "int8" \
+        else "fp64: DMMA (mma.sync.m8n8k4.f64)"
+    return cfg
+
+
+def _workload_config(args):
     if args.workload == "nigp":
         return {"workload": "configs[2]: NIGP noisy-input SE-ARD GP (sigma_x-derived per-point noise), N=%d train, "
                             "%d test points per GPU (a 16M-point set sharded over 8 GPUs), posterior mean + variance "
@@ -311,6 +319,8 @@ def run_ours(args):
         core.set_chunk(args.chunk)
         core.set_hypers(MF2_PARAMS, 1e-8)
         core.set_data(X4, y)
+    mode = L.MODE_INT8 if args.mode == "int8" else L.MODE_FP64
+    core.set_mode(mode)
     t0 = time.perf_counter()
     if world > 1:
         from gpcore.sharding import broadcast_factor
@@ -383,6 +393,7 @@ def run_ours(args):
         wrap.lengthscales_, wrap.sigma_f_, wrap.sigma_y_ = NIGP_HYP["ls"], NIGP_HYP["sigma_f"], NIGP_HYP["sigma_y"]
         wrap.sigma_x_, wrap.X_train_, wrap.y_train_, wrap.noise_diag_train_ = NIGP_HYP["sigma_x"], X4[:, :3], y, noise_diag
         wrap._factor().set_chunk(args.chunk)
+        wrap._factor().set_mode(mode)
         pinned = torch.from_numpy(np.ascontiguousarray(Xs4_host[:, :3])).pin_memory()
         Xs_pinned = pinned.numpy()
         api = "gpcore.nigp.NIGP.predict(Xs) -> gpc_predict (host pointers)"
@@ -397,6 +408,7 @@ def run_ours(args):
         model.param_array[:] = MF2_PARAMS
         wrap = GPyMultiOutputWrapper(model, F, n_optimization_restarts=1)
         model._ensure_factor().set_chunk(args.chunk)
+        model._ensure_factor().set_mode(mode)
         pinned = torch.from_numpy(Xs4_host).pin_memory()
         Xs_pinned = pinned.numpy()
         api = "gpcore.emukit GPyMultiOutputWrapper.predict(X4) -> gpc_predict (host pointers, pinned)"
@@ -434,31 +446,63 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
-    peak, peak_src = 35.46, "fallback: cuBLAS DGEMM 8192^3 measured on this pool's B200 in round 1"
+    dgemm_peak, dgemm_src = 35.46, "fallback: cuBLAS DGEMM 8192^3 measured on this pool's B200 in round 1"
     try:
         pk = json.load(open(DGEMM_PEAK_FILE))
-        peak = float(pk["dgemm_8192_tflops"])
-        peak_src = "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/microbench/dgemm_peak_r01.json); " \
-                   "MEASURED_PEAKS.json has no FP64 entry"
+        dgemm_peak = float(pk["dgemm_8192_tflops"])
+        dgemm_src = "measured: cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/microbench/dgemm_peak_r01.json); " \
+                    "MEASURED_PEAKS.json has no FP64 entry"
     except Exception:
         pass
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same config only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "k_vt_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01",
+                                         "k_vt_i8_traffic.json" if args.mode == "int8" else "k_vt_traffic.json")))
         if tr["n_train"] == N and tr["chunk_rows"] == args.chunk and not nigp_mode:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
     rows_per_launch = M * args.steps / max(hot_n, 1)
-    alg_flops_per_launch = rows_per_launch * float(N) * float(N)
+    alg_flops_per_launch = rows_per_launch * float(N) * float(N)     # FP64 algorithmic work: N^2 per point
     avg_ms = hot_ms / max(hot_n, 1)
-    achieved = alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "k_vt<false,true> (V = L^-1 K*, FP64 DMMA, fused sum of squares)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "launches": hot_n, "avg_launch_ms": avg_ms,
-                "algorithmic_flops_per_launch": alg_flops_per_launch,
-                "executed_flops_per_launch": hot_flops / max(hot_n, 1),
-                "share_of_step": hot_ms / ms}
+    fp64_equiv = alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
+    if args.mode == "int8":
+        # 21 exact int8 digit GEMMs stand in for the FP64 contraction: report the kernel against the INT8 tensor peak
+        i8_peak = 4560.0   # TOP/s, tcgen05.mma kind::i8 N >= 128 measured on this B200 (profiles/r01/umma_i8_rate_r01.txt)
+        achieved = 21.0 * alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "k_vt_i8<false,true> (V = L^-1 K* as 21 exact INT8 digit GEMMs, tcgen05 + TMEM, "
+                                                 "fused recombination and sum of squares)",
+                    "achieved": achieved, "peak": i8_peak, "unit": "TOP/s (int8)", "frac": achieved / i8_peak, "traffic": traffic,
+                    "peak_source": "measured: tcgen05.mma.kind::i8 issue rate on this pool's B200 "
+                                   "(profiles/microbench/umma_i8_rate.cu, profiles/r01/umma_i8_rate_r01.txt); "
+                                   "MEASURED_PEAKS.json has no INT8 entry",
+                    "launches": hot_n, "avg_launch_ms": avg_ms,
+                    "algorithmic_ops_per_launch": 21.0 * alg_flops_per_launch,
+                    "executed_ops_per_launch": 21.0 * hot_flops / max(hot_n, 1),
+                    "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": dgemm_peak,
+                    "fp64_equivalent_over_dgemm_peak": fp64_equiv / dgemm_peak,
+                    "share_of_step": hot_ms / ms}
+    else:
+        roofline = {"bound": "tensor", "kernel": "k_vt<false,true> (V = L^-1 K*, FP64 DMMA, fused sum of squares)",
+                    "achieved": fp64_equiv, "peak": dgemm_peak, "unit": "TFLOP/s", "frac": fp64_equiv / dgemm_peak,
+                    "traffic": traffic, "peak_source": dgemm_src, "launches": hot_n, "avg_launch_ms": avg_ms,
+                    "algorithmic_flops_per_launch": alg_flops_per_launch,
+                    "executed_flops_per_launch": hot_flops / max(hot_n, 1),
+                    "share_of_step": hot_ms / ms}
+    # the same workload on the other contraction path, a short run for context
+    other = {}
+    try:
+        omode = L.MODE_FP64 if args.mode == "int8" else L.MODE_INT8
+        core.set_mode(omode)
+        for _ in range(2):
+            step_dev()
+        barrier()
+        oms = timed(step_dev, 2, 0) if dist is None else None
+        if oms:
+            other = {"mode": "fp64" if args.mode == "int8" else "int8", "value": M * 2 / (oms * 1e-3), "ms_per_step": oms / 2}
+        core.set_mode(mode)
+    except Exception as exc:   # context only
+        other = {"error": str(exc)}
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------
     cpu = None
@@ -480,6 +524,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(M * 16),
                     "api": api},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "mode": args.mode, "other_mode": other,
             "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast}
 
     if args.ig and not nigp_mode:
@@ -529,6 +574,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mf2", choices=["mf2", "nigp"])
+    ap.add_argument("--mode", default="int8", choices=["int8", "fp64"],
+                    help="variance contraction: int8 = Ozaki digits on the tcgen05 INT8 tensor cores (default), "
+                         "fp64 = DMMA")
     ap.add_argument("--n-train", type=int, default=0)
     ap.add_argument("--m-test", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=16384)

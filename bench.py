@@ -489,20 +489,21 @@ def run_ours(args):
                     "algorithmic_flops_per_launch": alg_flops_per_launch,
                     "executed_flops_per_launch": hot_flops / max(hot_n, 1),
                     "share_of_step": hot_ms / ms}
-    # the same workload on the other contraction path, a short run for context
+    # the same workload on the other contraction path, a short run for context (single-GPU runs only:
+    # this block runs on rank 0 alone and must not touch a collective)
     other = {}
-    try:
-        omode = L.MODE_FP64 if args.mode == "int8" else L.MODE_INT8
-        core.set_mode(omode)
-        for _ in range(2):
-            step_dev()
-        barrier()
-        oms = timed(step_dev, 2, 0) if dist is None else None
-        if oms:
+    if dist is None:
+        try:
+            omode = L.MODE_FP64 if args.mode == "int8" else L.MODE_INT8
+            core.set_mode(omode)
+            for _ in range(2):
+                step_dev()
+            torch.cuda.synchronize()
+            oms = timed(step_dev, 2, 0)
             other = {"mode": "fp64" if args.mode == "int8" else "int8", "value": M * 2 / (oms * 1e-3), "ms_per_step": oms / 2}
-        core.set_mode(mode)
-    except Exception as exc:   # context only
-        other = {"error": str(exc)}
+            core.set_mode(mode)
+        except Exception as exc:   # context only
+            other = {"error": str(exc)}
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------
     cpu = None

@@ -14,6 +14,7 @@
 #include "gpc_ig.cuh"
 #include "gpc_ozaki.cuh"
 #include "gpc_predict.cuh"
+#include "gpc_traj.cuh"
 
 #define GPC_VERSION 100
 
@@ -984,6 +985,54 @@ int gpc_spd_stats(gpc_handle h, const double* cov, long M, const double* e, doub
   if (quad) *quad = e ? sc[2] : 0.0;
   if (fro_inv) *fro_inv = std::sqrt(f2 > 0.0 ? f2 : 0.0);
   return GPC_OK;
+}
+
+int gpc_traj_points(gpc_handle h, long C, const long* edge_off, const double* edge_xy, const long* prim_off,
+                    const double* prims, double variance_rate, double meas_rate, int dense, int with_var, double t_off,
+                    const double* fid_levels, int max_pts, double* pts, double* fid, long* counts) {
+  if (!h || !edge_off || !edge_xy || !prim_off || !prims || !pts || !counts) return GPC_ERR_ARG;
+  if (C < 0 || max_pts < 1) return fail(h, GPC_ERR_SHAPE, "bad path set");
+  if (!(meas_rate > 0.0)) return fail(h, GPC_ERR_ARG, "meas_rate must be positive");
+  if (C == 0) return GPC_OK;
+  CK(cudaSetDevice(h->device));
+  const long E = edge_off[C], P = prim_off[E];
+  for (long c = 0; c < C; ++c)
+    if (edge_off[c + 1] - edge_off[c] > GPC_TRAJ_MAXEDGE) return fail(h, GPC_ERR_SHAPE, "a path has more than 32 edges");
+  DevBuf d_eo, d_xy, d_po, d_pr, d_wp, d_pts, d_fid, d_cnt;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](DevBuf& b, size_t n) { if (e == cudaSuccess) e = b.ensure(n ? n : 8); };
+  alloc(d_eo, (size_t)(C + 1) * 8); alloc(d_xy, (size_t)E * 32); alloc(d_po, (size_t)(E + 1) * 8);
+  alloc(d_pr, (size_t)P * 32); alloc(d_wp, (size_t)(P + E) * 32); alloc(d_pts, (size_t)C * max_pts * 40);
+  alloc(d_fid, (size_t)C * max_pts * 8); alloc(d_cnt, (size_t)C * 8);
+  int rc = GPC_OK;
+  if (e != cudaSuccess) {
+    rc = fail(h, GPC_ERR_CUDA, cudaGetErrorString(e));
+  } else {
+    cudaStream_t s = h->stream;
+    cudaMemcpyAsync(d_eo.p, edge_off, (size_t)(C + 1) * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_xy.p, edge_xy, (size_t)E * 32, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_po.p, prim_off, (size_t)(E + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (P) cudaMemcpyAsync(d_pr.p, prims, (size_t)P * 32, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(d_pts.p, 0, (size_t)C * max_pts * 40, s);
+    cudaMemsetAsync(d_fid.p, 0, (size_t)C * max_pts * 8, s);
+    k_traj_points<<<(unsigned)C, 128, 0, s>>>(static_cast<const long*>(d_eo.p), d_xy.d(), static_cast<const long*>(d_po.p),
+                                             d_pr.d(), d_wp.d(), variance_rate, meas_rate, dense, with_var, t_off,
+                                             fid_levels ? fid_levels[0] : 0.0, fid_levels ? fid_levels[1] : 0.0,
+                                             fid_levels ? 1 : 0, max_pts, d_pts.d(), fid ? d_fid.d() : nullptr,
+                                             static_cast<long*>(d_cnt.p));
+    ++h->launches;
+    cudaMemcpyAsync(pts, d_pts.p, (size_t)C * max_pts * 40, cudaMemcpyDeviceToHost, s);
+    if (fid) cudaMemcpyAsync(fid, d_fid.p, (size_t)C * max_pts * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(counts, d_cnt.p, (size_t)C * 8, cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(h, GPC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  DevBuf* all[] = {&d_eo, &d_xy, &d_po, &d_pr, &d_wp, &d_pts, &d_fid, &d_cnt};
+  for (DevBuf* b : all) b->release();
+  if (rc == GPC_OK)
+    for (long c = 0; c < C; ++c)
+      if (counts[c] > max_pts) return fail(h, GPC_ERR_SHAPE, "a path produced more points than max_pts (counts[] holds the sizes)");
+  return rc;
 }
 
 void* gpc_stream(gpc_handle h) { return h ? (void*)h->stream : nullptr; }

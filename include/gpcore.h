@@ -164,6 +164,20 @@ int gpc_ig_selfgrid(gpc_handle h, const double* Xc4, const long* offsets, long C
 /* The IG calls time their dominant kernel (the same L^-1 K* contraction) through the
  * gpc_hot_kernel_time hooks below. */
 
+/* ---- candidate generation (GraceRIGV3.py:235-294 evaluateTraj, :373-427 edgePointsToTrajPoints /
+ *      pathToTrajPoints, :508-512 fidelity labels) -------------------------------------------------- */
+/* Path c owns edges edge_off[c] .. edge_off[c+1]-1 (<= 32); edge e has start/end node positions
+ * edge_xy[e] = (x0, y0, x1, y1) and the motion primitives prim_off[e] .. prim_off[e+1]-1, each
+ * (type, a, b, c): 0 spiral (dz, _, speed), 1 glide (pitch, dz, speed), 2 swim (dist, speed), 3 flat dive
+ * (dz, speed).  dense != 0 resamples every edge at meas_rate (np.arange / np.interp), otherwise the
+ * way-points themselves are returned; rows equal after rounding to 4 decimals are dropped keeping the
+ * first.  pts is C x max_pts x 5 (x, y, z, t, var); fid (C x max_pts, may be NULL) is the fidelity
+ * index from fid_levels (2 if var < fl[0], 1 if fl[0] < var < fl[1], else 0); counts[c] = points of path c.
+ * GPC_ERR_SHAPE when a path yields more than max_pts points (counts[] then tells the sizes). */
+int gpc_traj_points(gpc_handle h, long C, const long* edge_off, const double* edge_xy, const long* prim_off,
+                    const double* prims, double variance_rate, double meas_rate, int dense, int with_var,
+                    double t_off, const double* fid_levels, int max_pts, double* pts, double* fid, long* counts);
+
 /* ---- evaluator (GPTrainers.py:121-137) -------------------------------------------------------- */
 /* For a symmetric positive-definite M x M matrix cov (host, row-major) and a vector e (M, may be
  * NULL): quad = e^T inv(cov) e, fro_inv = ||inv(cov)||_F, logdet = log det cov -- through one

@@ -12,6 +12,8 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs ``/root/reference``
   (``GPData_0.2_fieldMeas_0_T0_0.csv``, 709 rows, estimated positions) with hypers held fixed.
 * ``field_data.npz`` -- that dataset's columns (inputs for the SF / MF parity tests) and the
   reference's test grids (``exploreSimSettings.py:116-119``, ``exploreExpSettings.py:164-167``).
+* ``traj_paths.npz`` -- the reference's own ``GraceAgent.pathToTrajPoints`` / ``evaluateTraj``
+  (``GraceRIGV3.py:235-294,373-427``, imported through ``oracle/mpl_shim``) on seeded primitive chains.
 * ``gp_oracle.npz``  -- outputs of the NumPy restatement (``gp_oracle.py``; GPy / emukit arithmetic,
   PARITY UNPINNED) on the same data: SF / MF predictions, covariances, information gains.  These
   freeze the restatement so a later edit to the oracle cannot silently move the target.
@@ -51,9 +53,77 @@ def grid(specs):
     return np.array([gi.ravel("F") for gi in g]).T
 
 
+def traj_golden():
+    """``traj_paths.npz``: outputs of the reference's OWN ``GraceAgent.pathToTrajPoints`` (imported from
+    /root/reference/GraceRIGV3.py through an empty matplotlib stand-in, ``oracle/mpl_shim``) on seeded
+    random primitive chains, for dense / way-point mode with and without the variance column."""
+    import types
+    sys.path.insert(0, os.path.join(HERE, "mpl_shim"))
+    sys.path.insert(0, os.path.join(HERE, "gpy_shim"))
+    sys.path.insert(0, REF)
+    import GraceRIGV3 as IG
+    assert os.path.realpath(IG.__file__).startswith(REF)
+    ag = IG.GraceAgent()
+    ag.varianceRate, ag.measRate = 0.01, 0.2
+    names = ag.legTypes
+    rng = np.random.default_rng(2024)
+    V, E, paths = [], {}, []
+    for c in range(24):
+        ne = int(rng.integers(1, 4))
+        pos = rng.uniform([0, 0], [10, 20])
+        first = len(V)
+        V.append(types.SimpleNamespace(state=np.array([[pos[0]], [pos[1]]])))
+        path = []
+        for e in range(ne):
+            pos = pos + rng.normal(0, 2.0, 2)
+            V.append(types.SimpleNamespace(state=np.array([[pos[0]], [pos[1]]])))
+            prims = []
+            for _ in range(int(rng.integers(1, 6))):
+                kind = int(rng.integers(0, 4))
+                if kind == 0:
+                    prims.append((names[0], float(rng.uniform(-1, 2)), 0.0, float(rng.uniform(0.05, 0.3))))
+                elif kind == 1:
+                    prims.append((names[1], float(rng.uniform(0.3, 1.0)), float(rng.uniform(-1.5, 2)), float(rng.uniform(0.05, 0.3))))
+                elif kind == 2:
+                    prims.append((names[2], float(rng.uniform(0.2, 3.0)), float(rng.uniform(0.1, 0.5))))
+                else:
+                    prims.append((names[3], float(rng.uniform(-1, 2)), float(rng.uniform(0.05, 0.3))))
+            i1, i2 = first + e, first + e + 1
+            E[(i1, i2)] = [(i1, i2, 0.0, 0.0, 0.0, 0.0, prims)]
+            path.append((i1, i2, 0))
+        paths.append(path)
+    out = {}
+    edge_off, xy, prim_off, pr = [0], [], [0], []
+    for path in paths:
+        edge_off.append(edge_off[-1] + len(path))
+        for i1, i2, k in path:
+            xy.append([V[i1].state[0, 0], V[i1].state[1, 0], V[i2].state[0, 0], V[i2].state[1, 0]])
+            for q in E[(i1, i2)][k][-1]:
+                vals = [float(names.index(q[0]))] + [float(v) for v in q[1:]]
+                pr.append(vals + [0.0] * (4 - len(vals)))
+            prim_off.append(len(pr))
+    out.update(edge_off=np.array(edge_off), edge_xy=np.array(xy), prim_off=np.array(prim_off), prims=np.array(pr),
+               variance_rate=ag.varianceRate, meas_rate=ag.measRate)
+    for dense in (0, 1):
+        for wv in (0, 1):
+            rows, offs = [], [0]
+            for path in paths:
+                p = ag.pathToTrajPoints(V, E, path, dense=bool(dense), withVar=bool(wv))
+                rows.append(p)
+                offs.append(offs[-1] + len(p))
+            out["pts_d%d_v%d" % (dense, wv)] = np.concatenate(rows)
+            out["off_d%d_v%d" % (dense, wv)] = np.array(offs)
+    np.savez_compressed(os.path.join(OUT, "traj_paths.npz"), **out)
+    print("traj_paths:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter("ignore")
+    if "--traj-only" in sys.argv:
+        traj_golden()
+        return
+    traj_golden()
     ref = reference_nigp()
 
     # ---- (i) NIGP demo, seed 0 -------------------------------------------------------------

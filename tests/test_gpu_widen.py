@@ -254,3 +254,76 @@ def test_config1_gptrainers_flow_matches_published_results(gpcore_mod):
     assert abs(wm["sf"] - 0.07326736) < 1e-3 * 0.07326736
     assert abs(wm["sfTP"] - 0.07317822) < 1e-3 * 0.07317822
     assert wm["nisf"] < 1e-6
+
+
+def _random_paths(rng, n_paths):
+    paths = []
+    for _ in range(n_paths):
+        ne = int(rng.integers(1, 4))
+        pos = rng.uniform([0, 0], [10, 20])
+        path = []
+        for _ in range(ne):
+            nxt = pos + rng.normal(0, 2.0, 2)
+            prims, depth = [], 0.0
+            for _ in range(int(rng.integers(1, 6))):
+                kind = int(rng.integers(0, 4))
+                if kind == 0:
+                    dz = float(rng.uniform(-1, 2)); prims.append((0.0, dz, 0.0, float(rng.uniform(0.05, 0.3))))
+                elif kind == 1:
+                    dz = float(rng.uniform(-1.5, 2)); prims.append((1.0, float(rng.uniform(0.3, 1.0)), dz, float(rng.uniform(0.05, 0.3))))
+                elif kind == 2:
+                    prims.append((2.0, float(rng.uniform(0.2, 3.0)), float(rng.uniform(0.1, 0.5)), 0.0))
+                else:
+                    dz = float(rng.uniform(-1, 2)); prims.append((3.0, dz, float(rng.uniform(0.05, 0.3)), 0.0))
+            path.append((pos.copy(), nxt.copy(), prims))
+            pos = nxt
+        paths.append(path)
+    return paths
+
+
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("with_var", [True, False])
+def test_candidate_generation_matches_reference_restatement(gpcore_mod, dense, with_var):
+    """Device evaluateTraj / edgePointsToTrajPoints / pathToTrajPoints + fidelity labels against the
+    NumPy restatement of GraceRIGV3.py:235-294,373-427 (oracle/traj_oracle.py)."""
+    from gpcore import trajectory
+    from gpcore.infogain import label_fidelity
+    from oracle import traj_oracle as to
+    rng = np.random.default_rng(61)
+    paths = _random_paths(rng, 40)
+    paths.append([((1.0, 1.0), (2.0, 2.0), [(2.0, 0.0, 0.3, 0.0)])])          # zero-length swim: duplicate way-points
+    paths.append([((1.0, 1.0), (1.0, 3.0), [(3.0, 1.0, 0.1, 0.0), (3.0, -1.0, 0.1, 0.0)]),
+                  ((1.0, 3.0), (1.0, 1.0), [(3.0, 1.0, 0.1, 0.0), (3.0, -1.0, 0.1, 0.0)])])   # there and back again
+    fl = [0.05, 0.15, 0.3]
+    pts, fids = trajectory.paths_to_points(paths, 0.01, 0.2, dense=dense, with_var=with_var, fid_levels=fl, max_pts=256)
+    for c, path in enumerate(paths):
+        want = to.path_to_traj_points(path, 0.01, 0.2, dense=dense, with_var=with_var)
+        got = pts[c][:, :want.shape[1]]
+        assert got.shape == want.shape, (c, got.shape, want.shape)
+        assert np.max(np.abs(got - want), initial=0.0) < 1e-11, c
+        if with_var:
+            assert np.array_equal(fids[c], label_fidelity(want[:, 4], fl))
+    rows = trajectory.candidate_rows(paths[:5], 0.01, 0.2, fl, dense=dense, max_pts=256)
+    assert rows[0].shape[1] == 4 and set(np.unique(np.concatenate(rows)[:, 3])) <= {0.0, 1.0, 2.0}
+    with pytest.raises(ValueError):
+        trajectory.paths_to_points(paths[:3], 0.01, 5.0, dense=True, max_pts=4)
+    assert trajectory.paths_to_points([], 0.01, 0.2)[0] == []
+
+
+@pytest.mark.parametrize("dense", [0, 1])
+@pytest.mark.parametrize("wv", [0, 1])
+def test_candidate_generation_matches_reference_planner_golden(gpcore_mod, dense, wv):
+    """Device candidate generation against outputs of the reference's OWN GraceAgent.pathToTrajPoints
+    (tests/golden/traj_paths.npz -- pinned)."""
+    from gpcore import trajectory
+    g = golden("traj_paths.npz")
+    eo, po = g["edge_off"], g["prim_off"]
+    paths = [[(g["edge_xy"][e][:2], g["edge_xy"][e][2:], [tuple(p) for p in g["prims"][po[e]:po[e + 1]]])
+              for e in range(eo[c], eo[c + 1])] for c in range(len(eo) - 1)]
+    pts, _ = trajectory.paths_to_points(paths, float(g["variance_rate"]), float(g["meas_rate"]), dense=bool(dense),
+                                        with_var=bool(wv), max_pts=256)
+    want, off = g["pts_d%d_v%d" % (dense, wv)], g["off_d%d_v%d" % (dense, wv)]
+    for c in range(len(paths)):
+        w = want[off[c]:off[c + 1]]
+        got = pts[c][:, :w.shape[1]]
+        assert got.shape == w.shape and np.max(np.abs(got - w), initial=0.0) < 1e-11, c

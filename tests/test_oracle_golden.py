@@ -121,3 +121,29 @@ def test_published_rmse_sanity_band():
     gp = go.SFGP(d["Xh"], d["y"], np.array([4.0, 2.0, 3.0, 2.5, 0.05]))
     mu, _ = gp.predict(d["Xh"][:50])
     assert np.sqrt(np.mean((mu[:, 0] - d["y"][:50]) ** 2)) < 1.0
+
+
+def _golden_paths(g):
+    paths = []
+    eo, po = g["edge_off"], g["prim_off"]
+    for c in range(len(eo) - 1):
+        path = []
+        for e in range(eo[c], eo[c + 1]):
+            xy = g["edge_xy"][e]
+            path.append((xy[:2], xy[2:], [tuple(p) for p in g["prims"][po[e]:po[e + 1]]]))
+        paths.append(path)
+    return paths
+
+
+@pytest.mark.parametrize("dense", [0, 1])
+@pytest.mark.parametrize("wv", [0, 1])
+def test_trajectory_restatement_matches_reference_planner(dense, wv):
+    """oracle/traj_oracle.py against outputs of the reference's own GraceAgent.pathToTrajPoints
+    (tests/golden/traj_paths.npz, generated by importing /root/reference/GraceRIGV3.py)."""
+    from oracle import traj_oracle as to
+    g = golden("traj_paths.npz")
+    pts, off = g["pts_d%d_v%d" % (dense, wv)], g["off_d%d_v%d" % (dense, wv)]
+    for c, path in enumerate(_golden_paths(g)):
+        got = to.path_to_traj_points(path, float(g["variance_rate"]), float(g["meas_rate"]), dense=bool(dense), with_var=bool(wv))
+        want = pts[off[c]:off[c + 1]]
+        assert got.shape == want.shape and np.max(np.abs(got - want), initial=0.0) < 1e-12, c

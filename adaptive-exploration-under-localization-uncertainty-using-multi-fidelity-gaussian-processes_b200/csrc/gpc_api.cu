@@ -454,8 +454,12 @@ int gpc_create(int kind, int F, int device, gpc_handle* out) {
   h->kind = kind;
   h->F = F;
   h->device = device;
-  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  // the main stream outranks the side stream
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo);
+
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {

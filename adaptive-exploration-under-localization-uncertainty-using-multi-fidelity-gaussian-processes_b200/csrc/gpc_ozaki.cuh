@@ -88,6 +88,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
+// tcgen05.wait::ld with the loaded registers as in/out operands, so that no use of them can be
+// scheduled above the wait.
+__device__ __forceinline__ void tmem_wait3(int32_t (&a)[8], int32_t (&b)[8], int32_t (&c)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])
+               :
+               : "memory");
+}
+
+// exact int64 -> double for |x| < 2^51: one 64-bit integer add and one DADD instead of I2F.F64.S64
+__device__ __forceinline__ double i64_to_f64(long long x) {
+  return __longlong_as_double(x + 0x4338000000000000LL) - 6755399441055744.0;  // 2^52 + 2^51
+}
+
 // The S digit bytes of 16 consecutive values for slice p, packed as one 16-byte vector: u[] holds
 // v + DIGIT_BIAS (bytes = digits + 128, byte 0 least significant = slice S-1).
 __device__ __forceinline__ uint4 pack_slice(const unsigned long long (&u)[16], int p) {
@@ -165,6 +187,103 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   }
 }
 
+// exp(-q) for q >= 0, branch-free so that the eight columns a thread works on interleave in the FP64
+// pipe (the library exp() carries special-case branches that serialise them): k = rint(-q log2 e) by the
+// magic-number add, two-step Cody-Waite reduction to |r| <= ln2 / 2, degree-13 Taylor polynomial
+// (truncation 1.7e-16 relative at the interval edge), 2^k by an exponent-field add.  q is clamped at 700
+// (e^-700 = 1e-304 is zero against any digit or mean), so k >= -1010 and the result stays normal.
+__device__ __forceinline__ double gpc_exp_neg(double q) {
+  q = fmin(q, 700.0);
+  const double t = fma(q, -1.4426950408889634074, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -6.93147180369123816490e-01, -q);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;            // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// exp(-q[u]) for W independent arguments, written stage by stage so that the W dependency chains
+// advance together (W-way ILP in the FP64 pipe from a single warp; the library exp() carries
+// special-case branches that keep the columns of a thread from interleaving).  The stages are volatile
+// asm so that the compiler keeps them breadth-first instead of re-serialising the chains.
+__device__ __forceinline__ double fma_pinned(double a, double b, double c) {
+  double d;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+  return d;
+}
+
+template <int W>
+__device__ __forceinline__ void gpc_exp_neg_w(const double* __restrict__ qin, double* __restrict__ e) {
+  double q[W], t[W], r[W], p[W];
+#pragma unroll
+  for (int u = 0; u < W; ++u) q[u] = fmin(qin[u], 700.0);
+#pragma unroll
+  for (int u = 0; u < W; ++u) t[u] = fma_pinned(q[u], -1.4426950408889634074, 6755399441055744.0);
+#pragma unroll
+  for (int u = 0; u < W; ++u) r[u] = t[u] - 6755399441055744.0;       // kf
+#pragma unroll
+  for (int u = 0; u < W; ++u) q[u] = fma_pinned(r[u], -6.93147180369123816490e-01, -q[u]);
+#pragma unroll
+  for (int u = 0; u < W; ++u) r[u] = fma_pinned(r[u], -1.90821492927058770002e-10, q[u]);
+#pragma unroll
+  for (int u = 0; u < W; ++u) p[u] = fma_pinned(1.6059043836821613e-10, r[u], 2.08767569878681e-09);   // 1/13!, 1/12!
+#define GPC_EXP_STAGE(c)            \
+  _Pragma("unroll") for (int u = 0; u < W; ++u) p[u] = fma_pinned(p[u], r[u], c);
+  GPC_EXP_STAGE(2.505210838544172e-08)    // 1/11!
+  GPC_EXP_STAGE(2.755731922398589e-07)    // 1/10!
+  GPC_EXP_STAGE(2.7557319223985893e-06)   // 1/9!
+  GPC_EXP_STAGE(2.48015873015873e-05)     // 1/8!
+  GPC_EXP_STAGE(1.984126984126984e-04)    // 1/7!
+  GPC_EXP_STAGE(1.3888888888888889e-03)   // 1/6!
+  GPC_EXP_STAGE(8.333333333333333e-03)    // 1/5!
+  GPC_EXP_STAGE(4.1666666666666664e-02)   // 1/4!
+  GPC_EXP_STAGE(1.6666666666666666e-01)   // 1/3!
+  GPC_EXP_STAGE(0.5)
+  GPC_EXP_STAGE(1.0)
+  GPC_EXP_STAGE(1.0)
+#undef GPC_EXP_STAGE
+#pragma unroll
+  for (int u = 0; u < W; ++u)
+    e[u] = __hiloint2double(__double2hiint(p[u]) + (__double2loint(t[u]) << 20), __double2loint(p[u]));
+}
+
+
+// Byte B of four 48-bit values -> 4 digit bytes of one slice.
+template <int B>
+__device__ __forceinline__ uint32_t pack_bytes4(const unsigned long long (&u)[4]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = B < 4 ? (uint32_t)u[e] : (uint32_t)(u[e] >> 32);
+  constexpr uint32_t sel = (uint32_t)(B & 3) | ((uint32_t)(4 + (B & 3)) << 4);
+  return __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410) ^ 0x80808080u;
+}
+
+// Byte b (0 = least significant) of eight 48-bit values -> the 8 digit bytes of one slice (PRMT).
+template <int B>
+__device__ __forceinline__ uint2 pack_bytes8(const unsigned long long (&u)[8]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = B < 4 ? (uint32_t)u[e] : (uint32_t)(u[e] >> 32);
+  constexpr uint32_t sel = (uint32_t)(B & 3) | ((uint32_t)(4 + (B & 3)) << 4);   // bytes B of x, B of y -> low half
+  const uint32_t t01 = __byte_perm(w[0], w[1], sel), t23 = __byte_perm(w[2], w[3], sel);
+  const uint32_t t45 = __byte_perm(w[4], w[5], sel), t67 = __byte_perm(w[6], w[7], sel);
+  return make_uint2(__byte_perm(t01, t23, 0x5410) ^ 0x80808080u, __byte_perm(t45, t67, 0x5410) ^ 0x80808080u);
+}
+
 // ------------------------------------------------------------------------------------------
 // K* assembly straight into the A digit image (+ posterior mean, + optional mean gradients): the
 // FP64 cross-covariance never goes to HBM -- 7 bytes per element are written instead of 8.
@@ -183,7 +302,7 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
                                                   const double* __restrict__ alpha, long N, long n_pad,
                                                   const double* __restrict__ Xs4, long M, long m_pad, double sA,
                                                   int8_t* __restrict__ Aimg, double* __restrict__ meanpart,
-                                                  double* __restrict__ gradpart) {
+                                                  double* __restrict__ gradpart) {  // grid (m_pad / 128, nchunks)
   using namespace gpoz;
   __shared__ __align__(128) double tr[5][KI_COLS];
   __shared__ double hil[GPC_MAXF][4];
@@ -244,20 +363,28 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
 #pragma unroll 1
     for (int m = 0; m <= mmc; ++m) {
       const double c0 = hil[m][0], c1 = hil[m][1], c2 = hil[m][2], wm = wS[m][tid];
+      double q[8], e[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int j = c8 * 8 + u;
         const double sx = (tr[0][j] - ax) * c0, sy = (tr[1][j] - ay) * c1, sz = (tr[2][j] - az) * c2;
-        const double q = fma(sx, sx, fma(sy, sy, sz * sz));
-        double e;
-        if (base == 0) {
-          e = exp(-q);
-        } else {
-          const double rt = 1.7320508075688772 * sqrt(q);
-          e = (1.0 + rt) * exp(-rt);
-        }
-        const int fj = fi32[2 * j];
-        k[u] = fma(wm * (fj >= 0 ? hcoef[fj][m] : 0.0), e, k[u]);
+        q[u] = fma(sx, sx, fma(sy, sy, sz * sz));
+      }
+      if (base == 0) {
+        gpc_exp_neg_w<4>(q, e);
+        gpc_exp_neg_w<4>(q + 4, e + 4);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = 1.7320508075688772 * sqrt(q[u]);
+        gpc_exp_neg_w<4>(q, e);
+        gpc_exp_neg_w<4>(q + 4, e + 4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] *= 1.0 + q[u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int fj = fi32[2 * (c8 * 8 + u)];
+        k[u] = fma(wm * (fj >= 0 ? hcoef[fj][m] : 0.0), e[u], k[u]);
       }
     }
     unsigned long long v[8];
@@ -276,8 +403,13 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
     const long kb = (j0 >> 6) + (c8 >> 3);
     int8_t* dst = Aimg + (((long)mt * nkb + kb) * S) * (long)A_SLICE + (r >> 3) * 512 + ((c8 >> 1) & 3) * 128 +
                   (r & 7) * 16 + (c8 & 1) * 8;
-#pragma unroll
-    for (int p = 0; p < S; ++p) *reinterpret_cast<uint2*>(dst + (long)p * A_SLICE) = pack_slice8(v, p);
+    // slice p holds byte S - 1 - p of the 48-bit value
+    *reinterpret_cast<uint2*>(dst + 0L * A_SLICE) = pack_bytes8<5>(v);
+    *reinterpret_cast<uint2*>(dst + 1L * A_SLICE) = pack_bytes8<4>(v);
+    *reinterpret_cast<uint2*>(dst + 2L * A_SLICE) = pack_bytes8<3>(v);
+    *reinterpret_cast<uint2*>(dst + 3L * A_SLICE) = pack_bytes8<2>(v);
+    *reinterpret_cast<uint2*>(dst + 4L * A_SLICE) = pack_bytes8<1>(v);
+    *reinterpret_cast<uint2*>(dst + 5L * A_SLICE) = pack_bytes8<0>(v);
   }
   meanpart[(long)blockIdx.y * m_pad + n] = mu;
   if (WITH_GRAD) {
@@ -303,6 +435,7 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ double sb_tile[2][TN];   // row scales of the tile being drained (x 2^-56 sA), double-buffered
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int npair = (nb2 + 1) / 2;
   const long nkb_total = ld >> 6;
@@ -391,10 +524,16 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4 =====
+    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4, one thread owns one test row =====
+    // The MMA issuer cannot start the next tile before the accumulators are drained (6 x 64 of the 512
+    // TMEM columns: no room for a second set), so this loop is on the critical path: the row scales are
+    // staged while the MMAs still run, the TMEM loads of the next half-group are in flight during the
+    // arithmetic of the current one, and the accumulators are released right after the last load.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int et = tid - 64;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const double cs = COMB_SCALE * sA;
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mt = item / npair, p = item - mt * npair;
@@ -402,61 +541,52 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
       const int nseg = (jbs[1] < jbs[0]) ? 2 : 1;
       for (int sg = 0; sg < nseg; ++sg, ++tile) {
         const int jb = jbs[sg];
+        double* sbt = sb_tile[tile & 1];
+        if (et < TN) sbt[et] = sB[(long)jb * TN + et] * cs;   // V = comb 2^-56 sA sB[i]
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait_guarded(&tmem_full_bar, tile & 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
         double ss = 0.0;
         const long n = (long)mt * TM + row;
+        int32_t v0[8], v1[8], v2[8], w0[8], w1[8], w2[8];
+        tmem_ld8(lane_addr + 0 * TN, v0);
+        tmem_ld8(lane_addr + 1 * TN, v1);
+        tmem_ld8(lane_addr + 2 * TN, v2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 16) {
-          long long hi[16], lo[16];
-          {
-            int32_t v[16];
-            tmem_ld16(lane_addr + 0 * TN + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int c0 = 0; c0 < TN; c0 += 8) {
+          tmem_wait3(v0, v1, v2);
+          tmem_ld8(lane_addr + 3 * TN + c0, w0);
+          tmem_ld8(lane_addr + 4 * TN + c0, w1);
+          tmem_ld8(lane_addr + 5 * TN + c0, w2);
+          long long hi[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = v[j];
+          for (int j = 0; j < 8; ++j) hi[j] = (long long)v0[j] * 65536LL + (long long)v1[j] * 256LL + (long long)v2[j];
+          tmem_wait3(w0, w1, w2);
+          if (c0 + 8 < TN) {
+            tmem_ld8(lane_addr + 0 * TN + c0 + 8, v0);
+            tmem_ld8(lane_addr + 1 * TN + c0 + 8, v1);
+            tmem_ld8(lane_addr + 2 * TN + c0 + 8, v2);
+          } else {
+            // every accumulator of this tile has been read: hand TMEM back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar);
           }
+          // comb = sum_t C_t 256^(5-t) = hi 256^3 + lo
+          double vv[8];
 #pragma unroll
-          for (int t = 1; t < 3; ++t) {
-            int32_t v[16];
-            tmem_ld16(lane_addr + t * TN + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 256 + v[j];
-          }
-          {
-            int32_t v[16];
-            tmem_ld16(lane_addr + 3 * TN + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 16; ++j) lo[j] = v[j];
-          }
-#pragma unroll
-          for (int t = 4; t < S; ++t) {
-            int32_t v[16];
-            tmem_ld16(lane_addr + t * TN + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 256 + v[j];
-          }
-          // comb = sum_t C_t 256^(5-t) = hi 256^3 + lo ;  V = comb 2^-96 256^5 sA sB[i] = comb 2^-56 sA sB[i]
-          const double* sb = sB + (long)jb * TN + c0;
-          double vv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const double comb = fma((double)hi[j], 16777216.0, (double)lo[j]);
-            vv[j] = comb * (COMB_SCALE * sA) * sb[j];
+          for (int j = 0; j < 8; ++j) {
+            const long long lo = (long long)w0[j] * 65536LL + (long long)w1[j] * 256LL + (long long)w2[j];
+            const double comb = fma(i64_to_f64(hi[j]), 16777216.0, i64_to_f64(lo));
+            vv[j] = comb * sbt[c0 + j];
             ss = fma(vv[j], vv[j], ss);
           }
           if (STORE_V) {
             double* dst = Vt + n * ld + (long)jb * TN + c0;
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(vv[j], vv[j + 1]);
+            for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(vv[j], vv[j + 1]);
           }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar);
         if (SUMSQ) sumsq[(long)jb * m_pad + n] = ss;
       }
     }

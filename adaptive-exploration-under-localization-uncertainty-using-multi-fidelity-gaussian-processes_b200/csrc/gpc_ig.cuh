@@ -329,6 +329,179 @@ __global__ void __launch_bounds__(128) k_ig_selfgrid_cand(const __grid_constant_
   if (tid == 0) I_out[blockIdx.x] = (ok0 && ok1 && ok2) ? I : __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// ------------------------------------------------------------------------------------------
+// Log-det information gain with emukit's ELEMENT-WISE clip reproduced (calculatePathInfoEmuBatch,
+// PhysicalExperimentCode/GraceRIGV3.py:599-618: both determinants are taken of
+// GPyMultiOutputWrapper.predict_covariance(grid), which returns np.clip(cov, 1e-10, inf) -- every
+// negative posterior covariance between two grid points becomes 1e-10).  The clip is not a low-rank
+// change, so the determinant lemma of k_ig_logdet_cand does not apply: per candidate the G x G matrix
+//   A = clip(S0 - W W^T),   S0 = noise-inclusive grid covariance given the data,
+//   W = B L_c^-T,  B = cov(grid, candidate | data) (G x k),  L_c L_c^T = candidate covariance + noise
+// is formed and factored.  One CTA (256 threads) per candidate, persistent over the chunk:
+//   * W^T (k x GP) lives in shared memory;
+//   * a left-looking blocked Cholesky with 32-column panels: thread = matrix row, 32 accumulators in
+//     registers, the panel entries are generated on the fly (S0 row segment - W W^T, clipped), updated
+//     with the previous panels (L^T kept column-major in an L2-resident scratch so that the row-per-
+//     thread reads coalesce; the 32 x 32 block of multipliers is staged in shared memory), the
+//     diagonal block is factored by one warp, the rows below are solved in registers.
+// logdet = 2 sum log L_ii; NaN when the clipped matrix is not positive definite (the reference's
+// log(det) is nan or meaningless there).  Rows / columns G..GP-1 are an identity pad.
+//   out[c] = ldp ? 0.5 (*ldp - logdet) : logdet      (spans == NULL: one evaluation with k = 0 = the prior)
+// ------------------------------------------------------------------------------------------
+constexpr int GPC_CLIP_NB = 32;
+constexpr int GPC_CLIP_FIXED = GPC_MAXK * GPC_IG_LD + GPC_MAXK * 4 + 2 * GPC_CLIP_NB * (GPC_CLIP_NB + 1) + 18;  // doubles
+inline size_t ig_clip_smem(int kcap, int GP) { return ((size_t)GPC_CLIP_FIXED + (size_t)kcap * GP) * 8; }
+
+__global__ void __launch_bounds__(256, 1) k_ig_logdet_clip(const __grid_constant__ GpcHyp h,
+                                                           const GpcSpan* __restrict__ spans, int ncand,
+                                                           const double* __restrict__ Xr4,
+                                                           const double* __restrict__ Gram,
+                                                           const double* __restrict__ Bt, long ldb,
+                                                           const double* __restrict__ S0, long lds, int G, int GP,
+                                                           double* scratch, double clip_lo,
+                                                           const double* __restrict__ ldp, double* __restrict__ out) {
+  extern __shared__ double dsm[];
+  constexpr int NB = GPC_CLIP_NB, LDD = GPC_CLIP_NB + 1;
+  double* S = dsm;
+  double(*pt)[4] = reinterpret_cast<double(*)[4]>(S + GPC_MAXK * GPC_IG_LD);
+  double* D = S + GPC_MAXK * GPC_IG_LD + GPC_MAXK * 4;
+  double* Lp = D + NB * LDD;
+  double* red = Lp + NB * LDD;
+  int* flagp = reinterpret_cast<int*>(red + 16);
+  double* Wt = red + 18;
+  double* Lt = scratch + (size_t)blockIdx.x * GP * GP;   // Lt[j * GP + i] = L[i][j]
+  const int tid = threadIdx.x;
+  for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
+    __syncthreads();
+    int k = 0;
+    bool ok = true;
+    if (spans) {
+      const GpcSpan sp = spans[c];
+      k = sp.k;
+      if (k > 0) {
+        const int tile = sp.rs >> 7, r0 = sp.rs & 127;
+        const double* Gt = Gram + (long)tile * 128 * 128;
+        for (int e = tid; e < k * 4; e += blockDim.x) pt[e >> 2][e & 3] = Xr4[(long)(sp.rs + (e >> 2)) * 4 + (e & 3)];
+        __syncthreads();
+        for (int e = tid; e < k * k; e += blockDim.x) {
+          const int j = e / k, i = e % k;
+          if (i > j) continue;
+          double s = gpc_kval(h, pt[j][0], pt[j][1], pt[j][2], pt[j][3], pt[i][0], pt[i][1], pt[i][2], pt[i][3]) -
+                     Gt[(r0 + j) * 128 + r0 + i];
+          if (i == j) s += h.noise[gpc_fid(h, pt[j][3])] + h.jitter;
+          S[j * GPC_IG_LD + i] = s;
+        }
+        __syncthreads();
+        ok = ig_chol(S, k, flagp);
+        // W^T = L_c^-1 B^T, one grid column per thread
+        for (int i = tid; i < GP; i += blockDim.x) {
+          for (int t = 0; t < k; ++t) {
+            double v = (i < G) ? Bt[(long)(sp.rs + t) * ldb + i] : 0.0;
+            for (int s2 = 0; s2 < t; ++s2) v = fma(-S[t * GPC_IG_LD + s2], Wt[s2 * GP + i], v);
+            Wt[t * GP + i] = v / S[t * GPC_IG_LD + t];
+          }
+        }
+        __syncthreads();
+      }
+    }
+    double ldsum = 0.0;
+    int bad = 0;
+    for (int p0 = 0; p0 < GP; p0 += NB) {
+      for (int base = p0; base < GP; base += blockDim.x) {
+        const int i = base + tid;
+        const bool act = i < GP;
+        double acc[NB];
+        if (act) {
+          if (i < G) {
+            const double* srow = S0 + (long)i * lds + p0;
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) acc[cc] = (p0 + cc < G) ? srow[cc] : 0.0;
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) acc[cc] = (p0 + cc == i) ? 1.0 : 0.0;
+          }
+          for (int t = 0; t < k; ++t) {
+            const double w = Wt[t * GP + i];
+            const double* wp = Wt + t * GP + p0;
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) acc[cc] = fma(-w, wp[cc], acc[cc]);
+          }
+          if (i < G) {
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc)
+              if (p0 + cc < G) acc[cc] = fmax(acc[cc], clip_lo);
+          }
+        }
+        for (int j0 = 0; j0 < p0; j0 += NB) {
+          __syncthreads();
+          for (int e = tid; e < NB * NB; e += blockDim.x) Lp[(e >> 5) * LDD + (e & 31)] = Lt[(size_t)(j0 + (e >> 5)) * GP + p0 + (e & 31)];
+          __syncthreads();
+          if (act) {
+#pragma unroll 4
+            for (int jj = 0; jj < NB; ++jj) {
+              const double a = Lt[(size_t)(j0 + jj) * GP + i];
+#pragma unroll
+              for (int cc = 0; cc < NB; ++cc) acc[cc] = fma(-a, Lp[jj * LDD + cc], acc[cc]);
+            }
+          }
+        }
+        if (base == p0) {   // the 32 rows of the diagonal block are threads 0..31 of this chunk
+          __syncthreads();
+          if (tid < NB) {
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) D[tid * LDD + cc] = acc[cc];
+          }
+          __syncthreads();
+          if (tid < NB) {
+            const int lane = tid;
+            for (int j = 0; j < NB; ++j) {
+              const double d = D[j * LDD + j];
+              if (!(d > 0.0)) bad = 1;
+              const double sq = sqrt(d);
+              __syncwarp();
+              if (lane == j) D[j * LDD + j] = sq;
+              if (lane > j) D[lane * LDD + j] /= sq;
+              __syncwarp();
+              if (lane > j) {
+                const double a = D[lane * LDD + j];
+                for (int l = j + 1; l <= lane; ++l) D[lane * LDD + l] = fma(-a, D[l * LDD + j], D[lane * LDD + l]);
+              }
+              __syncwarp();
+            }
+            ldsum += log(D[lane * LDD + lane]);
+          }
+          __syncthreads();
+        }
+        if (act) {
+          if (i >= p0 + NB) {
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) {
+              double v = acc[cc];
+#pragma unroll
+              for (int c2 = 0; c2 < cc; ++c2) v = fma(-acc[c2], D[cc * LDD + c2], v);
+              acc[cc] = v / D[cc * LDD + cc];
+            }
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) Lt[(size_t)(p0 + cc) * GP + i] = acc[cc];
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) Lt[(size_t)(p0 + cc) * GP + i] = (cc <= i - p0) ? D[(i - p0) * LDD + cc] : 0.0;
+          }
+        }
+      }
+    }
+    // threads 0..31 hold the log-diagonal partial sums and the not-PD flags
+    if (tid < 32) {
+      ldsum = warp_sum(ldsum);
+      bad = __any_sync(0xffffffffu, bad);
+      if (tid == 0) {
+        const double ld = (ok && !bad) ? 2.0 * ldsum : __longlong_as_double(0x7ff8000000000000LL);
+        out[c] = ldp ? 0.5 * (*ldp - ld) : ld;
+      }
+    }
+  }
+}
+
 // best[0] = argmax_c I[c] (first index on ties, NaNs ignored; -1 when every value is NaN or C == 0).
 __global__ void __launch_bounds__(1024) k_argmax(const double* __restrict__ I, long C, long* __restrict__ best) {
   __shared__ double sv[32];

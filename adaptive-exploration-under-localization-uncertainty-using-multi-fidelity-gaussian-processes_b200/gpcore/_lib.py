@@ -83,6 +83,7 @@ SIGNATURES = {
     "gpc_ig_seq": (C.c_int, [_h, _dp, _lp, C.c_long, C.c_double, C.c_int, C.c_uint, _ubp, _dp, _lp]),
     "gpc_ig_selfgrid": (C.c_int, [_h, _dp, _lp, C.c_long, C.c_int, C.c_uint, _dp, _lp]),
     "gpc_ig_logdet": (C.c_int, [_h, _dp, C.c_long, _dp, _lp, C.c_long, _dp, _dp, _lp]),
+    "gpc_ig_logdet_ex": (C.c_int, [_h, _dp, C.c_long, _dp, _lp, C.c_long, C.c_uint, _dp, _dp, _lp]),
     "gpc_traj_points": (C.c_int, [_h, C.c_long, _lp, _dp, _lp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
                                   _dp, C.c_int, _dp, _dp, _lp]),
     "gpc_spd_stats": (C.c_int, [_h, _dp, C.c_long, _dp, _dp, _dp, _dp]),

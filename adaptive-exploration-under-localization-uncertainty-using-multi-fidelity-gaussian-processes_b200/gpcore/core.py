@@ -185,15 +185,17 @@ class GPCore:
                                           L.CLIP_COV if clip else 0, L.dptr(I), C.byref(best)))
         return I[:Cn], best.value
 
-    def ig_logdet(self, grid4, rows4, offsets):
+    def ig_logdet(self, grid4, rows4, offsets, clip=False):
+        """clip=True: both determinants are taken of covariances clipped element-wise at 1e-10
+        (emukit ``predict_covariance``; ``calculatePathInfoEmuBatch``)."""
         grid4 = L.as_f64(grid4)
         rows4 = L.as_f64(rows4)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         Cn = offsets.size - 1
         I = np.empty(max(Cn, 1))
         best, prior = C.c_long(-1), C.c_double()
-        self._ck(self.lib.gpc_ig_logdet(self.h, L.dptr(grid4), grid4.shape[0], L.dptr(rows4), L.lptr(offsets), Cn,
-                                        L.dptr(I), C.byref(prior), C.byref(best)))
+        self._ck(self.lib.gpc_ig_logdet_ex(self.h, L.dptr(grid4), grid4.shape[0], L.dptr(rows4), L.lptr(offsets), Cn,
+                                           L.CLIP_COV if clip else 0, L.dptr(I), C.byref(prior), C.byref(best)))
         return I[:Cn], prior.value, best.value
 
     # -- evaluator ------------------------------------------------------------------------

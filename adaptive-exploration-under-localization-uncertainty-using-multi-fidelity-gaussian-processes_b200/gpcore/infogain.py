@@ -76,15 +76,16 @@ def seq_info_gain(model, cands, sig_n, pred_fid=-1, first_preadded=False, masks=
                        L.IG_FIRST_PREADDED if first_preadded else 0, mask)
 
 
-def logdet_info_gain(model, grid, cands):
+def logdet_info_gain(model, grid, cands, clip=False):
     """Raw I_c = 0.5 (logdet S_prior(grid) - logdet S_post(grid | data u X_c)) for every candidate,
-    S = noise-inclusive predictive covariance.  Returns (I (C,), logdet_prior, argmax)."""
+    S = noise-inclusive predictive covariance (clip=True: clipped element-wise at 1e-10 like emukit's
+    ``predict_covariance``).  Returns (I (C,), logdet_prior, argmax)."""
     core, m = _model_core(model)
     mf = not isinstance(m, GPRegression)
     grid = np.asarray(grid, dtype=float)
     g4 = to_x4(grid[:, :3], grid[:, 3]) if mf else to_x4(grid[:, :3])
     rows, offs = GPCore._ragged(_rows(cands, mf))
-    return core.ig_logdet(g4, rows, offs)
+    return core.ig_logdet(g4, rows, offs, clip=clip)
 
 
 def selfgrid_info_gain(model, cands, pred_fid=2, clip=True):
@@ -247,11 +248,12 @@ class InfoGainOperators:
         return float(self.calcPathInfoSFBatch_many(V, E, [path], dense)[0])
 
     def calculatePathInfoEmuBatch_many(self, V, E, paths, dense=False):
-        """``Phys/GraceRIGV3.py:599-618``: grid at fidelity 2, no guards, no clamp."""
+        """``Phys/GraceRIGV3.py:599-618``: grid at fidelity 2, no guards, no clamp; both covariances come
+        from emukit's ``predict_covariance``, i.e. clipped element-wise at 1e-10 (reproduced on the device)."""
         pts = [self._mf_points(V, E, p, dense, bounded_top=True) for p in paths]
         grid = np.asarray(self.fieldGrid, dtype=float)
         grid4 = np.hstack([grid[:, :3], 2 * np.ones((grid.shape[0], 1))])
-        I_raw, ldp, _ = logdet_info_gain(self.mfgp, grid4, pts)
+        I_raw, ldp, _ = logdet_info_gain(self.mfgp, grid4, pts, clip=True)
         if self.logDetPrior is None:
             self.logDetPrior = ldp
         return np.asarray(I_raw)

@@ -153,6 +153,14 @@ int gpc_ig_seq(gpc_handle h, const double* Xc4, const long* offsets, long C, dou
  * logdet S_prior.  G <= 4096. */
 int gpc_ig_logdet(gpc_handle h, const double* grid4, long G, const double* Xc4, const long* offsets,
                   long C, double* I_out, double* logdet_prior, long* best);
+/* The same with flags.  GPC_CLIP_COV reproduces emukit's GPyMultiOutputWrapper.predict_covariance, which
+ * returns np.clip(cov, 1e-10, inf): calculatePathInfoEmuBatch (PhysicalExperimentCode/GraceRIGV3.py:599-618)
+ * takes BOTH determinants of element-wise clipped G x G matrices (every negative posterior covariance
+ * between two grid points becomes 1e-10), so each candidate costs one G x G factorisation instead of
+ * a k x k determinant-lemma update; logdet_prior is then the log-det of the clipped prior.  NaN for a
+ * candidate whose clipped matrix is not positive definite.  Needs k_max * round_up(G, 32) <= ~22000. */
+int gpc_ig_logdet_ex(gpc_handle h, const double* grid4, long G, const double* Xc4, const long* offsets,
+                     long C, unsigned flags, double* I_out, double* logdet_prior, long* best);
 /* "Self-grid" log-det IG (calculatePathInfoEmu2, GraceRIGV3.py:505-523): the grid is the candidate
  * itself queried at pred_fid (>= 0; < 0 = each point's own fidelity),
  *   I_c = 0.5 (logdet K(Xp) - logdet S_post(Xp | data u X_c)),

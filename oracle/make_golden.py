@@ -14,6 +14,8 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs ``/root/reference``
   reference's test grids (``exploreSimSettings.py:116-119``, ``exploreExpSettings.py:164-167``).
 * ``traj_paths.npz`` -- the reference's own ``GraceAgent.pathToTrajPoints`` / ``evaluateTraj``
   (``GraceRIGV3.py:235-294,373-427``, imported through ``oracle/mpl_shim``) on seeded primitive chains.
+* ``ig_operators.npz`` -- the reference's own path-cost operators (root and PhysicalExperimentCode
+  ``GraceRIGV3.py``), run unmodified over adapters of the restated GP models.
 * ``gp_oracle.npz``  -- outputs of the NumPy restatement (``gp_oracle.py``; GPy / emukit arithmetic,
   PARITY UNPINNED) on the same data: SF / MF predictions, covariances, information gains.  These
   freeze the restatement so a later edit to the oracle cannot silently move the target.
@@ -117,13 +119,140 @@ def traj_golden():
     print("traj_paths:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
 
 
+def ig_operator_golden():
+    """``ig_operators.npz``: the reference's OWN path-cost operators (``GraceRIGV3.py:443-562`` and
+    ``PhysicalExperimentCode/GraceRIGV3.py:446-678``), imported and run unmodified, with the GP model
+    objects they call replaced by thin GPy / emukit-shaped adapters over ``gp_oracle`` (GPy and emukit are
+    not installable).  This pins the OPERATOR logic -- loops, pre-appends, windows, fidelity labels, guards --
+    to the reference's code; the GP arithmetic underneath stays the (unpinned) restatement."""
+    import copy
+    import importlib.util
+    import types
+    sys.path.insert(0, os.path.join(HERE, "mpl_shim"))
+    sys.path.insert(0, os.path.join(HERE, "gpy_shim"))
+    sys.path.insert(0, REF)
+    sys.path.insert(0, ROOT)
+    import GraceRIGV3 as IGroot
+    from oracle import gp_oracle as go
+    spec = importlib.util.spec_from_file_location("GraceRIGV3_phys", os.path.join(REF, "PhysicalExperimentCode", "GraceRIGV3.py"))
+    sys.path.insert(0, os.path.join(REF, "PhysicalExperimentCode"))
+    IGphys = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(IGphys)
+
+    class SF:
+        def __init__(self, X, Y, params):
+            self.params = np.asarray(params, float)
+            self.Gaussian_noise = types.SimpleNamespace(variance=np.array([self.params[-1]]))
+            self.kern = types.SimpleNamespace(lengthscale=self.params[1:4].copy(), variance=np.array([self.params[0]]))
+            self.set_XY(X, Y)
+
+        def set_XY(self, X, Y):
+            self.X, self.Y = np.asarray(X, float), np.asarray(Y, float).reshape(-1, 1)
+            self._gp = go.SFGP(self.X, self.Y, self.params, gram=False)
+
+        def predict(self, Xn, full_cov=False):
+            return self._gp.predict(np.asarray(Xn, float), full_cov=bool(full_cov))
+
+        def copy(self):
+            return copy.deepcopy(self)
+
+    class MF:
+        def __init__(self, X4, Y, params):
+            self.params = np.asarray(params, float)
+            v, ls, rho, _ = go.split_mf_params(self.params, 3)
+            kern = types.SimpleNamespace(rbf=types.SimpleNamespace(lengthscale=ls[0].copy()),
+                                         K=lambda A: go.k_ar1(A, A, v, ls, rho, gram=False, same=True))
+            self.gpy_model = types.SimpleNamespace(param_array=self.params, kern=kern)
+            self.set_data(X4, Y)
+
+        def set_data(self, X4, Y):
+            self.X, self.Y = np.asarray(X4, float), np.asarray(Y, float).reshape(-1, 1)
+            self._gp = go.MFGP(self.X, self.Y, self.params, F=3, gram=False)
+
+        def predict(self, X4):
+            return self._gp.predict(np.asarray(X4, float))
+
+        def predict_covariance(self, X4):
+            return self._gp.predict_covariance(np.asarray(X4, float))
+
+        def copy(self):
+            return copy.deepcopy(self)
+
+    fld = load_field()
+    sel = np.r_[0:60, 300:360, 600:660]                       # 180 points, all three fidelity levels
+    Xh, yv, lev = fld["Xh"][sel], fld["y"][sel], fld["fidLev"][sel]
+    sf_params = np.array([4.0, 2.0, 3.0, 2.5, 0.05])
+    mf_params = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+    X4 = np.hstack([Xh, (3 - lev)[:, None].astype(float)])     # fidLev 3/2/1 -> index 0/1/2 (GPTrainers.py:55-61)
+    g = np.load(os.path.join(OUT, "traj_paths.npz"))
+    eo, po = g["edge_off"], g["prim_off"]
+    names = ["Spiral", "Glide", "Swim", "FlatDive"]
+    V, E, paths = [], {}, []
+    for c in range(10):
+        path = []
+        for e in range(eo[c], eo[c + 1]):
+            xy = g["edge_xy"][e]
+            i1 = len(V); V.append(types.SimpleNamespace(state=np.array([[xy[0]], [xy[1]]])))
+            i2 = len(V); V.append(types.SimpleNamespace(state=np.array([[xy[2]], [xy[3]]])))
+            prims = []
+            for q in g["prims"][po[e]:po[e + 1]]:
+                k = int(q[0])
+                prims.append((names[k],) + tuple(float(v) for v in (q[1:4] if k < 2 else q[1:3])))
+            E[(i1, i2)] = [(i1, i2, 0.0, 0.0, 0.0, 0.0, prims)]
+            path.append((i1, i2, 0))
+        paths.append(path)
+    grid_ig = grid([[0, 10, 5], [0, 20, 4], [0, 10, 3]])       # a small field grid (60 points)
+    fid_levs = [0.05, 0.15, 0.3]
+    out = dict(Xh=Xh, y=yv, X4=X4, sf_params=sf_params, mf_params=mf_params, grid=grid_ig, fidLevs=np.array(fid_levs),
+               n_paths=len(paths), variance_rate=0.01, meas_rate=0.2)
+
+    def agent_for(mod):
+        ag = mod.GraceAgent()
+        ag.varianceRate, ag.measRate, ag.fidLevs, ag.fieldGrid = 0.01, 0.2, fid_levs, grid_ig
+        ag.sfgp, ag.mfgp = SF(Xh, yv, sf_params), MF(X4, yv, mf_params)
+        return ag
+
+    root, phys = agent_for(IGroot), agent_for(IGphys)
+    ops = {"root_calcPathInfoSF2": lambda p: root.calcPathInfoSF2(V, E, p),
+           "root_calcPathInfoSF": lambda p: root.calcPathInfoSF(V, E, p),
+           "root_calculatePathInfoEmu": lambda p: root.calculatePathInfoEmu(V, E, p),
+           "root_calculatePathInfoEmu2": lambda p: root.calculatePathInfoEmu2(V, E, p),
+           "phys_calcPathInfoSF4": lambda p: phys.calcPathInfoSF4(V, E, p),
+           "phys_calculatePathInfoEmu": lambda p: phys.calculatePathInfoEmu(V, E, p)}
+    for name, fn in ops.items():
+        vals = []
+        for p in paths:
+            for ag in (root, phys):                          # every call starts from the agent's own data
+                ag.sfgp, ag.mfgp = SF(Xh, yv, sf_params), MF(X4, yv, mf_params)
+                if hasattr(ag, "sfgp2"):
+                    ag.sfgp2 = None
+            vals.append(float(fn(p)))
+        out[name] = np.array(vals)
+        print(name, np.round(out[name][:4], 6))
+    for name in ("calcPathInfoSFBatch", "calculatePathInfoEmuBatch"):
+        vals = []
+        for p in paths:
+            phys.sfgp, phys.mfgp = SF(Xh, yv, sf_params), MF(X4, yv, mf_params)
+            phys.sfgp2 = None
+            phys.mfgp2 = None
+            phys.logDetPrior = None
+            vals.append(float(getattr(phys, name)(V, E, p)))
+        out["phys_" + name] = np.array(vals)
+        print(name, np.round(out["phys_" + name][:4], 6))
+    np.savez_compressed(os.path.join(OUT, "ig_operators.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter("ignore")
     if "--traj-only" in sys.argv:
         traj_golden()
         return
+    if "--ig-only" in sys.argv:
+        ig_operator_golden()
+        return
     traj_golden()
+    ig_operator_golden()
     ref = reference_nigp()
 
     # ---- (i) NIGP demo, seed 0 -------------------------------------------------------------

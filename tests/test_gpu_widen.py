@@ -327,3 +327,83 @@ def test_candidate_generation_matches_reference_planner_golden(gpcore_mod, dense
         w = want[off[c]:off[c + 1]]
         got = pts[c][:, :w.shape[1]]
         assert got.shape == w.shape and np.max(np.abs(got - w), initial=0.0) < 1e-11, c
+
+
+def test_info_gain_operators_match_reference_operator_code(gpcore_mod):
+    """Full device pipeline (paths -> candidate points -> information gain) against golden values produced
+    by the reference's OWN operators (root and PhysicalExperimentCode GraceRIGV3.py run unmodified over
+    adapters of the restated GP models; tests/golden/ig_operators.npz)."""
+    from gpcore import trajectory
+    from gpcore.GPy.kern import RBF
+    from gpcore.GPy.models import GPRegression
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    from gpcore.infogain import InfoGainOperators
+    g, t = golden("ig_operators.npz"), golden("traj_paths.npz")
+    eo, po = t["edge_off"], t["prim_off"]
+    edges = {c: [(t["edge_xy"][e][:2], t["edge_xy"][e][2:], [tuple(p) for p in t["prims"][po[e]:po[e + 1]]])
+                 for e in range(eo[c], eo[c + 1])] for c in range(int(g["n_paths"]))}
+
+    class Agent(InfoGainOperators):
+        fidLevs = list(g["fidLevs"])
+
+        def pathToTrajPoints(self, V, E, path, dense=False, t_off=0, withVar=False):
+            pts, _ = trajectory.paths_to_points([E[path]], float(g["variance_rate"]), float(g["meas_rate"]), dense=dense,
+                                                with_var=withVar, t_off=t_off, max_pts=256)
+            return pts[0] if withVar else pts[0][:, :4]
+
+    ag = Agent()
+    ag.fieldGrid = g["grid"]
+    ag.sfgp = GPRegression(g["Xh"], g["y"][:, None], RBF(3, ARD=True))
+    ag.sfgp.param_array[:] = g["sf_params"]
+    k = LinearMultiFidelityKernel([RBF(3, ARD=True) for _ in range(3)])
+    ag.mfgp = GPyMultiOutputWrapper(GPyLinearMultiFidelityModel(g["X4"], g["y"][:, None], k, n_fidelities=3), 3, 1)
+    ag.mfgp.gpy_model.param_array[:] = g["mf_params"]
+    paths = list(edges)
+    cases = [("root_calcPathInfoSF2", "calcPathInfoSF2", {}),
+             ("root_calcPathInfoSF", "calcPathInfoSF", {}),
+             ("phys_calcPathInfoSF4", "calcPathInfoSF4", {}),
+             ("root_calculatePathInfoEmu", "calculatePathInfoEmu", {"sig_index": -3}),
+             ("phys_calculatePathInfoEmu", "calculatePathInfoEmu", {"sig_index": -1}),
+             ("root_calculatePathInfoEmu2", "calculatePathInfoEmu2", {}),
+             ("phys_calcPathInfoSFBatch", "calcPathInfoSFBatch", {}),
+             ("phys_calculatePathInfoEmuBatch", "calculatePathInfoEmuBatch", {})]
+    for gold, op, kw in cases:
+        ag.logDetPrior = None
+        I, best = ag.score_many(None, edges, paths, operator=op, **kw)
+        want = g[gold]
+        assert normwise(I, want, 1.0) < 1e-7, (gold, I, want)
+        assert best == int(np.argmax(want)), gold
+
+
+def test_ig_logdet_emukit_clip(gpcore_mod, go):
+    """calculatePathInfoEmuBatch takes both determinants of emukit's predict_covariance, i.e. of G x G
+    matrices clipped element-wise at 1e-10 (PhysicalExperimentCode/GraceRIGV3.py:608-617).  The device path
+    with GPC_CLIP_COV against the literal refit loop of the oracle (clip active: the posterior covariance
+    between distant grid points is negative), on a small grid and on the reference's 10 x 6 x 5 grid."""
+    L_ = gpcore_mod._lib
+    g = golden("gp_oracle.npz")
+    rng = np.random.default_rng(77)
+    core = gpcore_mod.GPCore(L_.KIND_MF_AR1_RBF, 3, 0)
+    core.set_hypers(MF_PARAMS, 1e-8)
+    core.set_data(g["X4"], g["y4"])
+    core.factor()
+    ref = go.MFGP(g["X4"], g["y4"], MF_PARAMS, F=3, gram=False)
+    ks = [1, 5, 0, 17, 32, 33, 64]
+    cands = [np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (k, 3)), rng.integers(0, 3, (k, 1)).astype(float)]) for k in ks]
+    rows, offs = gpcore_mod.GPCore._ragged(cands)
+    ax = [np.linspace(0, 10, 10), np.linspace(0, 20, 6), np.linspace(0, 10, 5)]
+    big = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+    for grid in (rng.uniform([0, 0, 0], [10, 20, 10], (45, 3)), big):
+        g4 = np.hstack([grid, 2 * np.ones((len(grid), 1))])
+        cov0 = ref.predict_covariance(g4, clip_cov=None)
+        assert (cov0 < 1e-10).any()                         # the clip is active on this problem
+        I, prior, best = core.ig_logdet(g4, rows, offs, clip=True)
+        want = np.array([go.ig_logdet_refit(ref, g4, c, clip_cov=1e-10) if len(c) else 0.0 for c in cands])
+        assert abs(prior - np.linalg.slogdet(ref.predict_covariance(g4, clip_cov=1e-10))[1]) < 1e-8 * abs(prior)
+        assert normwise(I, want, 1.0) < 1e-8, (I, want)
+        assert best == int(np.argmax(want))
+        J, _, _ = core.ig_logdet(g4, rows, offs, clip=False)  # and the unclipped value differs
+        assert np.max(np.abs(J - I)) > 1e-6
+    core.close()

@@ -146,13 +146,35 @@ class InfoGainOperators:
 
     calcPathInfoSF3 = calcPathInfoSF2  # ``Phys/GraceRIGV3.py:471-496``: same arithmetic, cached copy
 
+    # A conditioning set far away from everything: zero covariance with every point (exp(-huge) == 0.0), so a
+    # model holding only this row behaves exactly like an EMPTY training set.
+    _FAR = 1.0e9
+
+    def _window_model(self, slot, model, X, keep, set_data):
+        """Cached copy of ``model`` conditioned on the rows of X inside the window (targets zero); a single
+        far-away row stands in for an empty window."""
+        inner = getattr(model, "gpy_model", model)
+        stamp = (inner.param_array.tobytes(), inner._data_version)
+        if getattr(self, "_%s_window_stamp" % slot, None) != stamp:
+            wm = model.copy()
+            Xw = X[keep]
+            if Xw.shape[0] == 0:
+                Xw = np.full((1, X.shape[1]), self._FAR)
+                if X.shape[1] == 4:
+                    Xw[0, 3] = 0.0
+            getattr(wm, set_data)(Xw, np.zeros((Xw.shape[0], 1)))
+            setattr(self, "_%s_window_model" % slot, wm)
+            setattr(self, "_%s_window_stamp" % slot, stamp)
+        return getattr(self, "_%s_window_model" % slot)
+
     def _sf_windowed_many(self, V, E, paths, dense, first_windowed):
-        """Windowed sequential SF variants.  ``first_windowed=False``: ``calcPathInfoSF``
-        (``GraceRIGV3.py:468-503``) -- the first point is scored against the full data (appended
-        first), later points against rows with x < 3 lx and y < 3 ly of data + appended points
-        (themselves included).  ``first_windowed=True``: ``calcPathInfoSF4``
-        (``Phys/GraceRIGV3.py:498-534``) -- the first point too is scored against the window, and
-        it is appended twice when it lies inside it (``:512-513``)."""
+        """Windowed sequential SF variants.  Row j of a path (j = 0 is the path's first point) is scored
+        against data + points 0..j -- the point itself included -- as long as that set has <= 100 rows
+        (N + 1 + j), and against its rows with x < 3 lx and y < 3 ly afterwards (the whole set when none
+        qualifies); row 0 always sees the whole set.  ``first_windowed=False``: ``calcPathInfoSF``
+        (``GraceRIGV3.py:468-503``).  ``first_windowed=True``: ``calcPathInfoSF4``
+        (``Phys/GraceRIGV3.py:498-534``) -- row 0 is scored against the window whatever the size, without
+        the empty-window fallback, and is appended twice when it lies inside it (``:512-513``)."""
         gp = self.sfgp
         pts = [self._sf_points(V, E, p, dense) for p in paths]
         sig_n = float(gp.Gaussian_noise.variance[0])
@@ -164,30 +186,29 @@ class InfoGainOperators:
         if not live:
             return out
         keep = inwin(gp.X)
-        if N + 2 <= 100 or not keep.any():
-            raise NotImplementedError("window fallbacks (<= 100 rows, empty window) are not batched")
-        stamp = (gp.param_array.tobytes(), gp._data_version)
-        if getattr(self, "_sf_window_stamp", None) != stamp:
-            self._sf_window_model = gp.copy()
-            self._sf_window_model.set_XY(gp.X[keep], np.zeros((int(keep.sum()), 1)))
-            self._sf_window_stamp = stamp
-        wm = self._sf_window_model
+        wm = self._window_model("sf", gp, gp.X, keep, "set_XY")
         P = [pts[c] for c in live]
         wmask = [np.where(inwin(p), COND | PRE, 0).astype(np.uint8) for p in P]
-        heads = [p[:1] for p in P]
-        # later points: sum over all rows on the windowed model minus the first row's own term
+        s0 = max(1, 100 - N)                        # first row whose set (N + 1 + j rows) exceeds 100
+        if keep.any():
+            sw = [min(s0, len(p)) for p in P]
+        else:                                       # empty window until the first path point falls inside it
+            first_in = [int(np.argmax(m > 0)) if (m > 0).any() else len(m) for m in wmask]
+            sw = [min(max(s0, f), len(p)) for f, p in zip(first_in, P)]
+        allpre = lambda n: np.full(n, COND | PRE, dtype=np.uint8)
+        I_full, _ = seq_info_gain(gp, [p[:s] for p, s in zip(P, sw)], sig_n, masks=[allpre(s) for s in sw])
         I_all, _ = seq_info_gain(wm, P, sig_n, masks=wmask)
-        I_head, _ = seq_info_gain(wm, heads, sig_n, masks=[m[:1] for m in wmask])
-        rest = np.asarray(I_all) - np.asarray(I_head)
+        I_head, _ = seq_info_gain(wm, [p[:s] for p, s in zip(P, sw)], sig_n, masks=[m[:s] for m, s in zip(wmask, sw)])
+        total = np.asarray(I_full) + np.asarray(I_all) - np.asarray(I_head)
         if first_windowed:
+            heads = [p[:1] for p in P]
             dup = [np.concatenate((h, h)) for h in heads]            # window copy (if inside) + the explicit append
             m2 = [np.array([m[0] & COND, COND | PRE], dtype=np.uint8) for m in wmask]
             I2, _ = seq_info_gain(wm, dup, sig_n, masks=m2)
             I1, _ = seq_info_gain(wm, heads, sig_n, masks=[np.array([m[0] & COND], dtype=np.uint8) for m in wmask])
-            first = np.asarray(I2) - np.asarray(I1)
-        else:
-            first, _ = seq_info_gain(gp, heads, sig_n, first_preadded=True)
-        out[live] = np.asarray(first) + rest
+            I0, _ = seq_info_gain(gp, heads, sig_n, masks=[allpre(1) for _ in heads])
+            total += np.asarray(I2) - np.asarray(I1) - np.asarray(I0)
+        out[live] = total
         return out
 
     def calcPathInfoSF_many(self, V, E, paths, dense=True):
@@ -204,29 +225,32 @@ class InfoGainOperators:
 
     def calculatePathInfoEmu_many(self, V, E, paths, dense=False, sig_index=-1, windowed=True):
         """``GraceRIGV3.py:525-562`` (``sig_index=-3``) / ``Phys/GraceRIGV3.py:641-678`` (``-1``).
-        windowed: once data + appended points exceed 100 the reference keeps only rows with
-        x < 5 lx and y < 5 ly -- and the point being predicted is then part of its own
-        conditioning set (``tempX`` is cut from ``allX`` after the append, ``:549-553``)."""
+        Point j is predicted (at fidelity 0) from data + points 0..j-1 while data + points 0..j have <= 100
+        rows; afterwards the reference keeps only rows with x < 5 lx and y < 5 ly of data + points 0..j --
+        the point being predicted is then part of its own conditioning set (``tempX`` is cut from ``allX``
+        after the append, ``:549-553``)."""
         pts = [self._mf_points(V, E, p, dense, bounded_top=False) for p in paths]
         gm = self.mfgp.gpy_model
         sig_n = float(gm.param_array[sig_index])
-        if not windowed or gm.X.shape[0] + 1 <= 100:
-            if windowed and any(gm.X.shape[0] + len(p) > 100 for p in pts):
-                raise NotImplementedError("window switch-over inside a candidate (N <= 100) is not batched")
-            I, _ = seq_info_gain(self.mfgp, pts, sig_n, pred_fid=0)
-            return np.asarray(I)
+        N = gm.X.shape[0]
+        s0 = max(0, 100 - N) if windowed else 1 << 30   # first windowed point
+        sw = [min(s0, len(p)) for p in pts]
+        I_full, _ = seq_info_gain(self.mfgp, [p[:s] for p, s in zip(pts, sw)], sig_n, pred_fid=0)
+        if all(s == len(p) for p, s in zip(pts, sw)):
+            return np.asarray(I_full)
         lx, ly = [float(v) for v in gm.kern.kernels[0].lengthscale[:2]]
         inwin = lambda X: np.logical_and(X[:, 0] < 5 * lx, X[:, 1] < 5 * ly)
-        wmodel = getattr(self, "_mf_window_model", None)
         keep = inwin(gm.X)
-        stamp = (gm.param_array.tobytes(), gm._data_version)
-        if wmodel is None or getattr(self, "_mf_window_stamp", None) != stamp:
-            wmodel = self.mfgp.copy()
-            wmodel.set_data(gm.X[keep], np.zeros((int(keep.sum()), 1)))
-            self._mf_window_model, self._mf_window_stamp = wmodel, stamp
         masks = [np.where(inwin(p), COND | PRE, 0).astype(np.uint8) for p in pts]
-        I, _ = seq_info_gain(wmodel, pts, sig_n, pred_fid=0, masks=masks)
-        return np.asarray(I)
+        if not keep.any():
+            for m, s in zip(masks, sw):
+                if s < len(m) and not (m[:s + 1] > 0).any():
+                    raise ValueError("empty conditioning window (the reference's set_data fails on it as well)")
+        wmodel = self._window_model("mf", self.mfgp, gm.X, keep, "set_data")
+        I_all, _ = seq_info_gain(wmodel, pts, sig_n, pred_fid=0, masks=masks)
+        I_head, _ = seq_info_gain(wmodel, [p[:s] for p, s in zip(pts, sw)], sig_n, pred_fid=0,
+                                  masks=[m[:s] for m, s in zip(masks, sw)])
+        return np.asarray(I_full) + np.asarray(I_all) - np.asarray(I_head)
 
     def calculatePathInfoEmu(self, V, E, path, dense=False, sig_index=-1):
         return float(self.calculatePathInfoEmu_many(V, E, [path], dense, sig_index)[0])

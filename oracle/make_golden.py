@@ -239,6 +239,33 @@ def ig_operator_golden():
             vals.append(float(getattr(phys, name)(V, E, p)))
         out["phys_" + name] = np.array(vals)
         print(name, np.round(out["phys_" + name][:4], 6))
+    # ---- small training sets: the sets of the windowed operators cross the 100-row threshold INSIDE a path
+    # (N = 60), and a training set with no row inside the x < 3 lx, y < 3 ly window (empty-window fallbacks)
+    def variant(tag, idx, names_):
+        Xs_, ys_, X4s_ = Xh[idx], yv[idx], X4[idx]
+        out[tag + "_idx"] = np.asarray(idx)
+        r_, p_ = IGroot.GraceAgent(), IGphys.GraceAgent()
+        for ag in (r_, p_):
+            ag.varianceRate, ag.measRate, ag.fidLevs, ag.fieldGrid = 0.01, 0.2, fid_levs, grid_ig
+        table = {"root_calcPathInfoSF": (r_, "calcPathInfoSF"), "phys_calcPathInfoSF4": (p_, "calcPathInfoSF4"),
+                 "root_calculatePathInfoEmu": (r_, "calculatePathInfoEmu"), "phys_calculatePathInfoEmu": (p_, "calculatePathInfoEmu")}
+        for nm in names_:
+            ag, meth = table[nm]
+            vals = []
+            for pth in paths:
+                ag.sfgp, ag.mfgp = SF(Xs_, ys_, sf_params), MF(X4s_, ys_, mf_params)
+                if hasattr(ag, "sfgp2"):
+                    ag.sfgp2 = None
+                vals.append(float(getattr(ag, meth)(V, E, pth)))
+            out[tag + "_" + nm] = np.array(vals)
+            print(tag, nm, np.round(out[tag + "_" + nm][:4], 6))
+
+    variant("n60", np.r_[0:20, 60:80, 120:140],
+            ["root_calcPathInfoSF", "phys_calcPathInfoSF4", "root_calculatePathInfoEmu", "phys_calculatePathInfoEmu"])
+    variant("n97", np.r_[0:33, 60:92, 120:152], ["root_calcPathInfoSF", "phys_calcPathInfoSF4", "root_calculatePathInfoEmu"])
+    far = np.where(np.logical_or(Xh[:, 0] >= 3 * sf_params[1], Xh[:, 1] >= 3 * sf_params[2]))[0]
+    variant("nowin", far[:120], ["root_calcPathInfoSF", "phys_calcPathInfoSF4"])
+    variant("nowin40", far[:40], ["root_calcPathInfoSF", "phys_calcPathInfoSF4"])
     np.savez_compressed(os.path.join(OUT, "ig_operators.npz"), **out)
 
 

@@ -547,7 +547,8 @@ def test_ig_agent_operators(gpcore_mod, go):
     ag.logDetPrior = None
     Jm = ag.calculatePathInfoEmuBatch_many(None, E, paths)
     g4 = np.hstack([d["ig_grid"], 2 * np.ones((len(d["ig_grid"]), 1))])
-    wantJm = np.array([go.ig_logdet_refit(refmf, g4, np.hstack([E[c][:, :3], label_fidelity(E[c][:, 4], ag.fidLevs)[:, None]]))
+    wantJm = np.array([go.ig_logdet_refit(refmf, g4, np.hstack([E[c][:, :3], label_fidelity(E[c][:, 4], ag.fidLevs)[:, None]]),
+                                          clip_cov=1e-10)      # emukit predict_covariance clips element-wise
                        for c in paths])
     assert normwise(Jm, wantJm, 1.0) < 1e-8
     # sequential MF, un-windowed core (calculatePathInfoEmu with the window switched off)

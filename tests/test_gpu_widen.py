@@ -375,6 +375,22 @@ def test_info_gain_operators_match_reference_operator_code(gpcore_mod):
         want = g[gold]
         assert normwise(I, want, 1.0) < 1e-7, (gold, I, want)
         assert best == int(np.argmax(want)), gold
+    # small training sets: the <= 100-row branches of the windowed operators (the switch to the window falls
+    # inside a path at N = 60 and N = 97) and a training set with no row inside the window
+    small = {"root_calcPathInfoSF": ("calcPathInfoSF", {}), "phys_calcPathInfoSF4": ("calcPathInfoSF4", {}),
+             "root_calculatePathInfoEmu": ("calculatePathInfoEmu", {"sig_index": -3}),
+             "phys_calculatePathInfoEmu": ("calculatePathInfoEmu", {"sig_index": -1})}
+    for tag in ("n60", "n97", "nowin", "nowin40"):
+        idx = g[tag + "_idx"]
+        ag.sfgp.set_XY(g["Xh"][idx], g["y"][idx][:, None])
+        ag.mfgp.set_data(g["X4"][idx], g["y"][idx][:, None])
+        for gold, (op, kw) in small.items():
+            if tag + "_" + gold not in g:
+                continue
+            I, best = ag.score_many(None, edges, paths, operator=op, **kw)
+            want = g[tag + "_" + gold]
+            assert normwise(I, want, 1.0) < 1e-7, (tag, gold, I, want)
+            assert best == int(np.argmax(want)), (tag, gold)
 
 
 def test_ig_logdet_emukit_clip(gpcore_mod, go):

@@ -258,8 +258,8 @@ class InfoGainOperators:
     # -- log-det variants ---------------------------------------------------------------------
     def calcPathInfoSFBatch_many(self, V, E, paths, dense=True):
         """``Phys/GraceRIGV3.py:571-597`` for many paths, each scored against the agent's current
-        data (the reference's cumulative append across calls, ``:590``, is a bug of its cached
-        copy and is not reproduced)."""
+        data (the cumulative append of the reference's cached copy, ``:590``, is reproduced by the
+        single-path ``calcPathInfoSFBatch`` only)."""
         pts = [self._sf_points(V, E, p, dense)[1:] for p in paths]
         I_raw, ldp, _ = logdet_info_gain(self.sfgp, self.fieldGrid, pts)
         G = np.asarray(self.fieldGrid).shape[0]
@@ -268,8 +268,44 @@ class InfoGainOperators:
             self.logDetPrior = ldp if LOG_DBL_MIN <= ldp <= LOG_DBL_MAX else (fallback if ldp < LOG_DBL_MIN else np.inf)
         return _guarded_sf_batch(I_raw, ldp, G, fallback)
 
+    # True: the single-path ``calcPathInfoSFBatch`` reproduces the reference's cached model copy, whose data
+    # GROW across the calls of one ``plan()`` (see there).  The batched ``*_many`` / ``score_many`` calls always
+    # score every path against the agent's current data only.
+    reference_quirks = True
+
     def calcPathInfoSFBatch(self, V, E, path, dense=True):
-        return float(self.calcPathInfoSFBatch_many(V, E, [path], dense)[0])
+        """``Phys/GraceRIGV3.py:571-597``.  The reference scores on a cached copy ``sfgp2`` that is reset to the
+        agent's data only while ``logDetPrior`` is None (once per ``plan()``, ``:581-582,1314``) and appends the
+        path's points to the COPY's data on every call (``:590``), so call c of a plan is conditioned on the
+        points of calls 0..c-1 as well.  With ``reference_quirks`` (default) this is reproduced: one device
+        refit + grid covariance + log-det per call; otherwise the path is scored independently."""
+        if not self.reference_quirks:
+            return float(self.calcPathInfoSFBatch_many(V, E, [path], dense)[0])
+        X = self._sf_points(V, E, path, dense)[1:]
+        grid = np.asarray(self.fieldGrid, dtype=float)
+        G = grid.shape[0]
+        m = getattr(self, "_sfb_model", None)
+        if m is None:
+            m = self._sfb_model = self.sfgp.copy()
+
+        def grid_logdet():
+            _, K = m.predict(grid, full_cov=True)
+            return m._ensure_factor().spd_stats(K)[2]
+
+        if self.logDetPrior is None:
+            m.set_XY(self.sfgp.X, self.sfgp.Y)
+            ld = grid_logdet()
+            if ld < LOG_DBL_MIN:        # det == 0 -> det of (variance + noise) I
+                ld = G * np.log(float(m.kern.variance[0]) + float(m.Gaussian_noise.variance[0]))
+            elif ld > LOG_DBL_MAX:
+                ld = np.inf
+            self.logDetPrior = ld
+        m.set_XY(np.concatenate((m.X, X)), np.concatenate((m.Y, np.zeros((X.shape[0], 1)))))
+        ld = grid_logdet()
+        ld = 0.0 if ld < LOG_DBL_MIN else (np.inf if ld > LOG_DBL_MAX else ld)
+        with np.errstate(invalid="ignore"):
+            I = max(0.5 * (self.logDetPrior - ld), 0)
+        return 0.0 if np.isinf(I) else float(I)
 
     def calculatePathInfoEmuBatch_many(self, V, E, paths, dense=False):
         """``Phys/GraceRIGV3.py:599-618``: grid at fidelity 2, no guards, no clamp; both covariances come

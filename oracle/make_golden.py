@@ -239,6 +239,12 @@ def ig_operator_golden():
             vals.append(float(getattr(phys, name)(V, E, p)))
         out["phys_" + name] = np.array(vals)
         print(name, np.round(out["phys_" + name][:4], 6))
+    # ---- calcPathInfoSFBatch as the planner drives it: logDetPrior reset once, then consecutive calls --
+    # the cached copy keeps the points of the earlier calls (PhysicalExperimentCode/GraceRIGV3.py:590)
+    phys.sfgp, phys.mfgp = SF(Xh, yv, sf_params), MF(X4, yv, mf_params)
+    phys.sfgp2, phys.logDetPrior = None, None
+    out["phys_calcPathInfoSFBatch_consecutive"] = np.array([float(phys.calcPathInfoSFBatch(V, E, p)) for p in paths])
+    print("consecutive", np.round(out["phys_calcPathInfoSFBatch_consecutive"][:4], 6))
     # ---- small training sets: the sets of the windowed operators cross the 100-row threshold INSIDE a path
     # (N = 60), and a training set with no row inside the x < 3 lx, y < 3 ly window (empty-window fallbacks)
     def variant(tag, idx, names_):

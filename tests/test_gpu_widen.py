@@ -375,6 +375,13 @@ def test_info_gain_operators_match_reference_operator_code(gpcore_mod):
         want = g[gold]
         assert normwise(I, want, 1.0) < 1e-7, (gold, I, want)
         assert best == int(np.argmax(want)), gold
+    # the single-path calcPathInfoSFBatch as the planner drives it: consecutive calls after one reset keep the
+    # points of the earlier calls in the cached copy (reference quirk, reproduced by default)
+    ag.logDetPrior = None
+    ag._sfb_model = None
+    got = np.array([ag.calcPathInfoSFBatch(None, edges, c) for c in paths])
+    assert normwise(got, g["phys_calcPathInfoSFBatch_consecutive"], 1.0) < 1e-7, (got, g["phys_calcPathInfoSFBatch_consecutive"])
+    assert np.max(np.abs(got[1:] - g["phys_calcPathInfoSFBatch"][1:])) > 1e-3      # and differs from independent scoring
     # small training sets: the <= 100-row branches of the windowed operators (the switch to the window falls
     # inside a path at N = 60 and N = 97) and a training set with no row inside the window
     small = {"root_calcPathInfoSF": ("calcPathInfoSF", {}), "phys_calcPathInfoSF4": ("calcPathInfoSF4", {}),

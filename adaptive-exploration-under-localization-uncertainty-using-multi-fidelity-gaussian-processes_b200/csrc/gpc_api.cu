@@ -47,7 +47,8 @@ std::string g_create_error;
 struct gpc_handle_s {
   int kind = 0, F = 1, device = 0;
   cudaStream_t stream = nullptr, side = nullptr;   // side: look-ahead stream of the factorisation
-  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  cudaStream_t inv = nullptr;                      // early part of the triangular inverse (runs under the Cholesky tail)
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_half = nullptr, ev_inv = nullptr;
   GpcHyp hyp;
   bool have_hyp = false, have_data = false, factored = false;
   long N = 0, n_pad = 0;
@@ -130,38 +131,70 @@ int set_gemm_attrs(gpc_handle h) {
 
 // Blocked right-looking Cholesky of the n_pad x n_pad matrix A (in place, lower) followed by the
 // triangular inverse X = L^-1 (recursive doubling, scratch T).  d_status: device int, 0 = PD.
-// Look-ahead: after the panel solve of block column p only block column p+1 of the trailing
-// matrix is updated on the main stream; the (serial, one-CTA) factorisation of diagonal block p+1
-// and its panel solve then run on the side stream while the main stream finishes the rest of the
-// rank-128 update, so the latency of the diagonal kernel hides behind the DMMA work.
+// Panels (128 columns) are processed in PAIRS: the trailing matrix is updated once per pair with a
+// rank-256 product (half the passes over the trailing matrix and a k-loop twice as long as a
+// rank-128 update).  Look-ahead: the update first covers the two block columns of the NEXT pair on
+// the main stream; the serial chain of that pair -- diagonal block (one CTA), panel solve, rank-128
+// update of the pair's second block column, second diagonal block, second panel solve -- then runs
+// on the side stream while the main stream finishes the rank-256 update of the rest.
 int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int* d_status) {
   const int nb = (int)(n_pad / 128);
   cudaStream_t s = h->stream, s2 = h->side;
+  const int half = nb / 2;
+  const bool early = nb >= 8 && (nb & (nb - 1)) == 0;   // power-of-two block count: the recursion splits at nb / 2
   CK(cudaMemsetAsync(d_status, 0, sizeof(int), s));
-  k_potrf_diag<<<1, 256, GPC_POTRF_SMEM, s>>>(A, X, n_pad, 0, d_status);
+  k_potrf_diag<<<1, GPC_PD_NT, GPC_POTRF_SMEM, s>>>(A, X, n_pad, 0, d_status);
   CKL();
-  for (int p = 0; p < nb; ++p) {
-    const int m = nb - p - 1;  // block rows below the diagonal
-    if (m == 0) break;
-    // panel p is solved on the stream that factored its diagonal block (main for p = 0, side otherwise)
-    cudaStream_t sp = (p == 0) ? s : s2;
-    k_trsm_panel<<<2 * m, gpc64::NT, gpc64::SMEM_BYTES, sp>>>(A, X, n_pad, p, 2 * (p + 1));
+  for (int p = 0; p + 1 < nb; p += 2) {
+    cudaStream_t sc = (p == 0) ? s : s2;   // the stream that factored diagonal block p carries the pair's chain
+    const int m = nb - p - 1;              // block rows below diagonal block p
+    k_trsm_panel<<<2 * m, gpc64::NT, gpc64::SMEM_BYTES, sc>>>(A, X, n_pad, p, 2 * (p + 1));
     CKL();
-    if (p > 0) {
+    k_syrk_panel<<<dim3(2, 2 * m), gpc64::NT, gpc64::SMEM_BYTES, sc>>>(A, n_pad, p, 2 * (p + 1), 2 * (p + 1), 128);
+    CKL();
+    k_potrf_diag<<<1, GPC_PD_NT, GPC_POTRF_SMEM, sc>>>(A, X, n_pad, p + 1, d_status);
+    CKL();
+    const int m2 = nb - p - 2;             // block rows / columns behind the pair
+    if (m2 <= 0) {
+      if (sc != s) {
+        CK(cudaEventRecord(h->ev_side, s2));
+        CK(cudaStreamWaitEvent(s, h->ev_side, 0));
+      }
+      break;
+    }
+    k_trsm_panel<<<2 * m2, gpc64::NT, gpc64::SMEM_BYTES, sc>>>(A, X, n_pad, p + 1, 2 * (p + 2));
+    CKL();
+    if (early && p + 2 == half) {
+      // block columns 0 .. half-1 of L are final: invert the leading half and form T[B, A] = L[B, A] X[A, A]
+      // of the top level on the third stream, under the (latency-bound) second half of the Cholesky
+      CK(cudaEventRecord(h->ev_half, sc));
+      CK(cudaStreamWaitEvent(h->inv, h->ev_half, 0));
+      for (int sb = 1; sb < half; sb *= 2)
+        for (int phase = 0; phase < 2; ++phase) {
+          k_linv_level<<<dim3(2 * sb, 2 * sb, half / (2 * sb)), gpc64::NT, gpc64::SMEM_BYTES, h->inv>>>(A, X, T, n_pad, nb, sb,
+                                                                                                   phase, 0);
+          CKL();
+        }
+      k_linv_level<<<dim3(2 * half, 2 * half, 1), gpc64::NT, gpc64::SMEM_BYTES, h->inv>>>(A, X, T, n_pad, nb, half, 0, 0);
+      CKL();
+      CK(cudaEventRecord(h->ev_inv, h->inv));
+    }
+    if (sc != s) {
       CK(cudaEventRecord(h->ev_side, s2));
       CK(cudaStreamWaitEvent(s, h->ev_side, 0));
     }
-    // block column p+1 of the trailing matrix first ...
-    k_syrk_panel<<<dim3(2, 2 * m), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, n_pad, p, 2 * (p + 1), 2 * (p + 1));
+    // rank-256 update with panels p, p+1: the next pair's two block columns first ...
+    const int la = m2 < 2 ? m2 : 2;
+    k_syrk_panel<<<dim3(2 * la, 2 * m2), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, n_pad, p, 2 * (p + 2), 2 * (p + 2), 256);
     CKL();
     CK(cudaEventRecord(h->ev_main, s));
     CK(cudaStreamWaitEvent(s2, h->ev_main, 0));
-    k_potrf_diag<<<1, 256, GPC_POTRF_SMEM, s2>>>(A, X, n_pad, p + 1, d_status);
+    k_potrf_diag<<<1, GPC_PD_NT, GPC_POTRF_SMEM, s2>>>(A, X, n_pad, p + 2, d_status);
     CKL();
-    // ... then the rest of it, concurrently with the next diagonal block
-    if (m > 1) {
-      k_syrk_panel<<<dim3(2 * (m - 1), 2 * (m - 1)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, n_pad, p, 2 * (p + 2),
-                                                                                       2 * (p + 2));
+    // ... then the rest, concurrently with the next pair's chain
+    if (m2 > la) {
+      k_syrk_panel<<<dim3(2 * (m2 - la), 2 * (m2 - la)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(
+          A, n_pad, p, 2 * (p + 2 + la), 2 * (p + 2 + la), 256);
       CKL();
     }
   }
@@ -169,10 +202,23 @@ int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int
     CK(cudaEventRecord(h->ev_side, s2));
     CK(cudaStreamWaitEvent(s, h->ev_side, 0));
   }
+  if (early) {
+    // the trailing half's own levels, then the second phase of the top level
+    for (int sb = 1; sb < half; sb *= 2)
+      for (int phase = 0; phase < 2; ++phase) {
+        k_linv_level<<<dim3(2 * sb, 2 * sb, half / (2 * sb)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, sb, phase,
+                                                                                           half / (2 * sb));
+        CKL();
+      }
+    CK(cudaStreamWaitEvent(s, h->ev_inv, 0));
+    k_linv_level<<<dim3(2 * half, 2 * half, 1), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, half, 1, 0);
+    CKL();
+    return GPC_OK;
+  }
   for (int sb = 1; sb < nb; sb *= 2) {
     const int nodes = (nb + 2 * sb - 1) / (2 * sb);
     for (int phase = 0; phase < 2; ++phase) {
-      k_linv_level<<<dim3(2 * sb, 2 * sb, nodes), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, sb, phase);
+      k_linv_level<<<dim3(2 * sb, 2 * sb, nodes), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, X, T, n_pad, nb, sb, phase, 0);
       CKL();
     }
   }
@@ -454,11 +500,16 @@ int gpc_create(int kind, int F, int device, gpc_handle* out) {
   h->kind = kind;
   h->F = F;
   h->device = device;
-  // the main stream outranks the side stream
+  // the side stream carries the latency-critical chain of the factorisation (diagonal blocks, panel solves):
+  // it outranks the main stream (bulk updates), which outranks the early-inverse stream
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo);
+  const int prio_mid = (prio_hi < prio_lo - 1) ? prio_hi + 1 : prio_lo;
+  e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_mid);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->inv, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_half, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming);
 
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming);
@@ -498,7 +549,10 @@ int gpc_destroy(gpc_handle h) {
   }
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->ev_half) cudaEventDestroy(h->ev_half);
+  if (h->ev_inv) cudaEventDestroy(h->ev_inv);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->inv) cudaStreamDestroy(h->inv);
   cudaStreamDestroy(h->stream);
   delete h;
   return GPC_OK;

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) k_assemble_train(const __grid_constant__ 
 #define GPC_PD_LD 129
 constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 32) * 8;
 
-__global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
+constexpr int GPC_PD_NT = 512;   // threads of the diagonal-block CTA
+__global__ void __launch_bounds__(GPC_PD_NT, 1) k_potrf_diag(double* __restrict__ A, double* __restrict__ X, long ld,
                                                        int p, int* __restrict__ status) {
   extern __shared__ double sm[];
   double* S = sm;  // L in the lower triangle (incl. diagonal), X^T above it
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
   __shared__ int bad;
   if (tid == 0) bad = 0;
 #pragma unroll 8
-  for (int e = tid; e < 128 * 128; e += 256) {
+  for (int e = tid; e < 128 * 128; e += GPC_PD_NT) {
     const int r = e >> 7, c = e & 127;
     const double v = (c <= r) ? Ap[(long)r * ld + c] : 0.0;
     if (c <= r) S[r * GPC_PD_LD + c] = v;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
     // (3) rank-16 updates in 4 x 4 micro-tiles: first the trailing Cholesky tiles (lower triangle of
     //     nt x nt), then the inverse's right-hand side Y[r][c] -= L[r][c0:c0+16] X[c0:c0+16][c], c < r0
     const int nt = nrow >> 2, nchol = nt * nt, ncx = r0 >> 2, ntot = nchol + nt * ncx;
-    for (int idx = tid; idx < ntot; idx += 256) {
+    for (int idx = tid; idx < ntot; idx += GPC_PD_NT) {
       double c[4][4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(double* __restrict__ A, d
   }
   if (bad && tid == 0) atomicCAS(status, 0, p + 1);
 #pragma unroll 8
-  for (int e = tid; e < 128 * 128; e += 256) {
+  for (int e = tid; e < 128 * 128; e += GPC_PD_NT) {
     const int r = e >> 7, c = e & 127;
     Ap[(long)r * ld + c] = (c <= r) ? S[r * GPC_PD_LD + c] : 0.0;
     Xp[(long)r * ld + c] = (c <= r) ? XT(r, c) : 0.0;
@@ -254,16 +255,16 @@ __global__ void __launch_bounds__(gpc64::NT, 4) k_trsm_panel(double* __restrict_
   gpc64::store_tile(Arow + 64, ld, acc1, 1.0, 0.0);
 }
 
-// Trailing update: A_ij -= L_ip L_jp^T over 64 x 64 tiles with row tile ti in [t_lo, t_hi) and column
+// Trailing update: A_ij -= L_i,[p..] L_j,[p..]^T (kdim = 128: panel p, 256: panels p and p+1) over 64 x 64 tiles with row tile ti in [t_lo, t_hi) and column
 // tile tj in [c_lo, c_hi), tj <= ti (all in units of 64 rows).  grid (c_hi - c_lo, t_hi - t_lo).
 __global__ void __launch_bounds__(gpc64::NT, 4) k_syrk_panel(double* __restrict__ A, long ld, int p, int t_lo,
-                                                             int c_lo) {
+                                                             int c_lo, int kdim) {
   extern __shared__ double sm[];
   const int tj = c_lo + blockIdx.x, ti = t_lo + blockIdx.y;
   if (tj > ti) return;
   double acc[4][4][2];
   gpcg::zero_acc(acc);
-  gpc64::mainloop<false>(A + (long)ti * 64 * ld + (long)p * 128, ld, A + (long)tj * 64 * ld + (long)p * 128, ld, 0, 128,
+  gpc64::mainloop<false>(A + (long)ti * 64 * ld + (long)p * 128, ld, A + (long)tj * 64 * ld + (long)p * 128, ld, 0, kdim,
                          acc, sm);
   gpc64::store_tile(A + (long)ti * 64 * ld + (long)tj * 64, ld, acc, -1.0, 1.0);
 }
@@ -273,13 +274,13 @@ __global__ void __launch_bounds__(gpc64::NT, 4) k_syrk_panel(double* __restrict_
 // blocks [a0, a0 + 2 sb) with split mid = a0 + sb:
 //   phase 0:  T[B, A] = L[B, A] * X[A, A]          (k over the A-range, >= the column tile)
 //   phase 1:  X[B, A] = - X[B, B] * T[B, A]        (k over the B-range, <= the row tile)
-// grid (2 sb, 2 sb, nodes) over 64 x 64 tiles; tiles past the matrix end exit.
+// grid (2 sb, 2 sb, nodes) over 64 x 64 tiles, nodes node0 .. node0 + gridDim.z - 1; tiles past the matrix end exit.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(gpc64::NT, 4) k_linv_level(const double* __restrict__ L, double* __restrict__ X,
                                                              double* __restrict__ T, long ld, int nb, int sb,
-                                                             int phase) {
+                                                             int phase, int node0) {
   extern __shared__ double sm[];
-  const int a0 = blockIdx.z * 2 * sb, mid = a0 + sb;           // in 128-blocks
+  const int a0 = (node0 + blockIdx.z) * 2 * sb, mid = a0 + sb;  // in 128-blocks
   const int aj = 2 * a0 + blockIdx.x;                          // column tile (64s) inside the A-range
   const int bi = 2 * mid + (2 * sb - 1 - (int)blockIdx.y);     // row tile (64s) inside the B-range, long k first
   if (bi >= 2 * nb) return;

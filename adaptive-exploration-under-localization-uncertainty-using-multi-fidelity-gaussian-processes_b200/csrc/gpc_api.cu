@@ -395,7 +395,9 @@ int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean,
     if (d_sx) CK(Gb[b]->ensure((size_t)nchunks * 3 * mp_max * 8));
   }
   CK(h->sumsq.ensure((size_t)(2 * h->nb) * mp_max * 8));
-  cudaStream_t s1 = h->stream, s2 = h->side;
+  // the assembly runs on the LOW-priority stream: when k_vt_i8 of chunk i and the assembly of chunk i+1 become
+  // runnable together, the contraction's persistent CTAs are placed first and the assembly fills in behind them
+  cudaStream_t s1 = h->stream, s2 = h->inv;
   CK(cudaEventRecord(h->ev_main, s1));       // the side stream starts after everything queued so far
   CK(cudaStreamWaitEvent(s2, h->ev_main, 0));
   const double sA = kstar_scale(h);

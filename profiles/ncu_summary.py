@@ -1,0 +1,33 @@
+"""Condense `ncu -i X.ncu-rep --page raw --csv` output to the metrics the profiles/ summaries quote.
+usage: ncu -i X.ncu-rep --page raw --csv | python profiles/ncu_summary.py > profiles/rNN/ncu_<kernel>.csv"""
+import csv
+import sys
+
+KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__cycles_elapsed.max"]
+rows = list(csv.reader(sys.stdin))
+hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+names, units, data = rows[hdr], rows[hdr + 1], rows[hdr + 2:]
+col = {n: i for i, n in enumerate(names)}
+w = csv.writer(sys.stdout)
+w.writerow(["metric", "unit"] + ["launch%d: %s %s" % (i, r[col["Kernel Name"]][:40], r[col.get("Grid Size", 0)]) for i, r in enumerate(data)])
+for m in KEEP:
+    if m in col:
+        w.writerow([m, units[col[m]]] + [r[col[m]] for r in data])

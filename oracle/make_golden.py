@@ -16,6 +16,7 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs ``/root/reference``
   (``GraceRIGV3.py:235-294,373-427``, imported through ``oracle/mpl_shim``) on seeded primitive chains.
 * ``ig_operators.npz`` -- the reference's own path-cost operators (root and PhysicalExperimentCode
   ``GraceRIGV3.py``), run unmodified over adapters of the restated GP models.
+* ``eid.npz`` -- the reference's own ``exploreSimSettings.getEID`` over adapters of the restated GP models.
 * ``gp_oracle.npz``  -- outputs of the NumPy restatement (``gp_oracle.py``; GPy / emukit arithmetic,
   PARITY UNPINNED) on the same data: SF / MF predictions, covariances, information gains.  These
   freeze the restatement so a later edit to the oracle cannot silently move the target.
@@ -275,17 +276,64 @@ def ig_operator_golden():
     np.savez_compressed(os.path.join(OUT, "ig_operators.npz"), **out)
 
 
+def eid_golden():
+    """``eid.npz``: the reference's own ``exploreSimSettings.getEID`` (imported from a scratch working directory --
+    the module writes ``Data/fieldSettings.txt`` at import) over adapters of the restated GP models."""
+    import tempfile
+    import types
+    sys.path.insert(0, os.path.join(HERE, "mpl_shim"))
+    sys.path.insert(0, os.path.join(HERE, "gpy_shim"))
+    sys.path.insert(0, REF)
+    sys.path.insert(0, ROOT)
+    from oracle import gp_oracle as go
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, "Data"))
+    os.chdir(tmp)
+    try:
+        import exploreSimSettings as ess
+    finally:
+        os.chdir(cwd)
+    fld = load_field()
+    sel = np.r_[0:60, 300:360, 600:660]
+    Xh, yv, lev = fld["Xh"][sel], fld["y"][sel], fld["fidLev"][sel]
+    sf_params = np.array([4.0, 2.0, 3.0, 2.5, 0.05])
+    mf_params = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+    X4 = np.hstack([Xh, (3 - lev)[:, None].astype(float)])
+    sf = go.SFGP(Xh, yv[:, None], sf_params, gram=False)
+    mf = go.MFGP(X4, yv[:, None], mf_params, F=3, gram=False)
+    sfa = types.SimpleNamespace(predict=lambda X: sf.predict(np.asarray(X, float)),
+                                kern=types.SimpleNamespace(variance=np.array([sf_params[0]])),
+                                Gaussian_noise=types.SimpleNamespace(variance=np.array([sf_params[-1]])))
+    mfa = types.SimpleNamespace(predict=lambda X: mf.predict(np.asarray(X, float)),
+                                gpy_model=types.SimpleNamespace(param_array=mf_params))
+    WS, mD = np.array([[0, 10], [0, 20]]), 10
+    out = dict(Xh=Xh, y=yv, X4=X4, sf_params=sf_params, mf_params=mf_params, WS=WS, mD=mD)
+    for auto in (0, 1):
+        ess.auto = auto
+        out["sf_auto%d" % auto], out["grid"] = ess.getEID(sfa, WS, mD)
+        out["mf_auto%d" % auto], _ = ess.getEID(mfa, WS, mD, emu=True)
+    ess.auto = 0
+    out["sf_alpha03"], _ = ess.getEID(sfa, WS, mD, alpha=0.3)   # (an ndarray testSet raises in the reference: `testSet==None`)
+    np.savez_compressed(os.path.join(OUT, "eid.npz"), **out)
+    print("eid:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter("ignore")
     if "--traj-only" in sys.argv:
         traj_golden()
         return
+    if "--eid-only" in sys.argv:
+        eid_golden()
+        return
     if "--ig-only" in sys.argv:
         ig_operator_golden()
         return
     traj_golden()
     ig_operator_golden()
+    eid_golden()
     ref = reference_nigp()
 
     # ---- (i) NIGP demo, seed 0 -------------------------------------------------------------

@@ -430,3 +430,24 @@ def test_ig_logdet_emukit_clip(gpcore_mod, go):
         J, _, _ = core.ig_logdet(g4, rows, offs, clip=False)  # and the unclipped value differs
         assert np.max(np.abs(J - I)) > 1e-6
     core.close()
+
+
+def test_getEID_on_device_models(gpcore_mod):
+    """The EID map through the mirrored SF / MF models (device predict) against the reference's getEID golden."""
+    from gpcore.eid import getEID
+    from gpcore.GPy.kern import RBF
+    from gpcore.GPy.models import GPRegression
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    g = golden("eid.npz")
+    sf = GPRegression(g["Xh"], g["y"][:, None], RBF(3, ARD=True))
+    sf.param_array[:] = g["sf_params"]
+    k = LinearMultiFidelityKernel([RBF(3, ARD=True) for _ in range(3)])
+    mf = GPyMultiOutputWrapper(GPyLinearMultiFidelityModel(g["X4"], g["y"][:, None], k, n_fidelities=3), 3, 1)
+    mf.gpy_model.param_array[:] = g["mf_params"]
+    for auto in (0, 1):
+        E, grid = getEID(sf, g["WS"], float(g["mD"]), auto=auto)
+        assert np.max(np.abs(E - g["sf_auto%d" % auto])) < 1e-8 * np.max(g["sf_auto%d" % auto])
+        E, _ = getEID(mf, g["WS"], float(g["mD"]), emu=True, auto=auto)
+        assert np.max(np.abs(E - g["mf_auto%d" % auto])) < 1e-8 * np.max(g["mf_auto%d" % auto])

@@ -147,3 +147,36 @@ def test_trajectory_restatement_matches_reference_planner(dense, wv):
         got = to.path_to_traj_points(path, float(g["variance_rate"]), float(g["meas_rate"]), dense=bool(dense), with_var=bool(wv))
         want = pts[off[c]:off[c + 1]]
         assert got.shape == want.shape and np.max(np.abs(got - want), initial=0.0) < 1e-12, c
+
+
+def test_getEID_host_logic_matches_reference():
+    """gpcore.eid.getEID (host part of the EID map) over oracle-backed adapters against golden values produced by
+    the reference's own exploreSimSettings.getEID (tests/golden/eid.npz)."""
+    import types
+    import __graft_entry__ as entry
+    entry.setup_path()
+    from gpcore.eid import getEID
+    from oracle import gp_oracle as go
+    g = golden("eid.npz")
+    sf = go.SFGP(g["Xh"], g["y"][:, None], g["sf_params"], gram=False)
+    mf = go.MFGP(g["X4"], g["y"][:, None], g["mf_params"], F=3, gram=False)
+    sfa = types.SimpleNamespace(predict=lambda X: sf.predict(np.asarray(X, float)),
+                                kern=types.SimpleNamespace(variance=np.array([g["sf_params"][0]])),
+                                Gaussian_noise=types.SimpleNamespace(variance=np.array([g["sf_params"][-1]])))
+    mfa = types.SimpleNamespace(predict=lambda X: mf.predict(np.asarray(X, float)),
+                                gpy_model=types.SimpleNamespace(param_array=g["mf_params"]))
+    for auto in (0, 1):
+        E, grid = getEID(sfa, g["WS"], float(g["mD"]), auto=auto)
+        assert np.array_equal(grid, g["grid"])
+        assert np.max(np.abs(E - g["sf_auto%d" % auto])) < 1e-12 * np.max(g["sf_auto%d" % auto])
+        E, _ = getEID(mfa, g["WS"], float(g["mD"]), emu=True, auto=auto)
+        assert np.max(np.abs(E - g["mf_auto%d" % auto])) < 1e-12 * np.max(g["mf_auto%d" % auto])
+    E, _ = getEID(sfa, g["WS"], float(g["mD"]), alpha=0.3)
+    assert np.max(np.abs(E - g["sf_alpha03"])) < 1e-12 * np.max(g["sf_alpha03"])
+    # experiment variant: negative variances are replaced by the prior variance, sqrt without abs
+    neg = types.SimpleNamespace(predict=lambda X: (np.zeros((len(X), 1)), np.where(np.arange(len(X))[:, None] % 7 == 0, -1e-6, 0.5)),
+                                kern=sfa.kern, Gaussian_noise=sfa.Gaussian_noise)
+    E, ss = getEID(neg, g["WS"], float(g["mD"]), variant="exp", alpha=0.2, default_grid=g["grid"][:100])
+    assert np.all(np.isfinite(E)) and abs(E.sum() - 1) < 1e-12 and ss.shape == (100, 3)
+    E, _ = getEID(neg, g["WS"], float(g["mD"]))                    # simulation variant: uniform map
+    assert np.allclose(E, 1.0 / E.shape[0])

@@ -222,7 +222,7 @@ def run_reference(args):
                                        "NumPy/SciPy restatement of the GPy/emukit arithmetic (neither is installable "
                                        "offline), BLAS threads = all host cores" % (M_sample, args.m_test, N, t_factor)},
             "e2e": {"value": pts_s, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 NIGP_HYP = dict(ls=np.array([2.0, 3.0, 2.5]), sigma_f=4.0, sigma_y=0.2, sigma_x=np.array([0.1, 0.1, 0.05]))
@@ -287,7 +287,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+            os.environ.pop("NCCL_DEBUG", None)     # NCCL prints its version banner to stdout at VERSION and above
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gpcore.build()
@@ -546,7 +546,7 @@ def run_ours(args):
 
     if args.ig and not nigp_mode:
         line["ig"] = bench_ig(args, gpcore, L, torch, local)
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -593,7 +593,29 @@ def bench_ig(args, gpcore, L, torch, local):
             "finite": bool(np.all(np.isfinite(I)) and np.all(np.isfinite(Is))), "best": int(best)}
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """Everything that native libraries write to fd 1 during the run (NCCL's version banner ...) goes to stderr:
+    stdout carries exactly the one JSON line."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _STDOUT_FD is not None:
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -74,6 +74,7 @@ struct gpc_handle_s {
   int n_sm = 0;
   // information-gain workspaces
   DevBuf gX4, gVt, gS, gSinv, gT, Bt, Zt, cand_off, cand_I, cand_aux, cand_rows, cand_mask, gram, gramZ;
+  DevBuf Vimg, gBimg, gsB, sV1, Pt;   // INT8 information gain: digit images of V (candidates) and of the grid's V, scales
   // hot-kernel timing
   bool hot_timing = false;
   std::vector<cudaEvent_t> ev;
@@ -123,8 +124,10 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_ig_logdet_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_ig_selfgrid_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
-  CK(cudaFuncSetAttribute(k_vt_i8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_vt_i8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device));
   return GPC_OK;
 }
@@ -328,7 +331,7 @@ int ensure_slices(gpc_handle h) {
   const long np = h->n_pad;
   CK(h->Bimg.ensure((size_t)np * np * gpoz::S));
   CK(h->sBv.ensure((size_t)np * 8));
-  k_slice_rows<<<(unsigned)(np / 8), 256, 0, h->stream>>>(h->X.d(), np, np, static_cast<int8_t*>(h->Bimg.p), h->sBv.d());
+  k_slice_rows<<<(unsigned)(np / 8), 256, 0, h->stream>>>(h->X.d(), np, np, static_cast<int8_t*>(h->Bimg.p), h->sBv.d(), np, 1);
   CKL();
   h->have_slices = true;
   return GPC_OK;
@@ -342,13 +345,18 @@ double kstar_scale(gpc_handle h) {
   return std::ldexp(1.0, e + 2);  // |k| / sA < 1/4
 }
 
-// V = K* X^T on the INT8 tensor cores for one chunk whose digit image is in h->Aimg.
-template <bool STORE_V, bool SUMSQ>
-int launch_vt_i8(gpc_handle h, const int8_t* Aimg, long m_pad, double* Vt, double* sumsq) {
-  const long np = h->n_pad;
-  const int nb2 = (int)(np / gpoz::TN);
-  const int n_items = (int)(m_pad / gpoz::TM) * ((nb2 + 1) / 2);
-  const int grid = n_items < h->n_sm ? n_items : h->n_sm;
+// Scale of the digits of V = L^-1 K*: sum_i V_i^2 <= k(x*, x*), so |V| <= sqrt(max prior variance).
+double v_scale(gpc_handle h) {
+  double kmax = 0.0;
+  for (int i = 0; i < h->F; ++i) kmax = std::fmax(kmax, h->hyp.kdiag[i]);
+  int e = 0;
+  std::frexp(std::sqrt(kmax), &e);
+  return std::ldexp(1.0, e + 2);  // |V| / sV < 1/4
+}
+
+template <int OUT, bool FULLK>
+int launch_i8(gpc_handle h, const VtI8Args& a, double fp64_equiv_flops) {
+  const int grid = a.n_items < h->n_sm ? a.n_items : h->n_sm;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->hot_timing) {
     if (h->ev_used + 2 > h->ev.size()) {
@@ -362,15 +370,84 @@ int launch_vt_i8(gpc_handle h, const int8_t* Aimg, long m_pad, double* Vt, doubl
     e1 = h->ev[h->ev_used++];
     CK(cudaEventRecord(e0, h->stream));
   }
-  k_vt_i8<STORE_V, SUMSQ><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(
-      Aimg, static_cast<const int8_t*>(h->Bimg.p), h->sBv.d(), kstar_scale(h), np, nb2,
-      m_pad, n_items, Vt, sumsq);
+  k_vt_i8<OUT, FULLK><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
   CKL();
   if (h->hot_timing) {
     CK(cudaEventRecord(e1, h->stream));
-    h->hot_flops += (double)m_pad * (double)np * (double)(np + 64);  // FP64-equivalent; x 21 digit GEMMs in int8 ops
+    h->hot_flops += fp64_equiv_flops;  // FP64-equivalent; x 21 digit GEMMs in int8 ops
   }
   return GPC_OK;
+}
+
+// V = K* X^T on the INT8 tensor cores for one chunk whose digit image is Aimg (triangular schedule).
+// OUT_SUMSQ: sumsq; OUT_F64: Vt [m_pad][n_pad]; OUT_DIGITS: Vimg, the digit image of V (scale v_scale).
+template <int OUT>
+int launch_vt_i8(gpc_handle h, const int8_t* Aimg, long m_pad, double* Vt, double* sumsq, int8_t* Vimg = nullptr) {
+  const long np = h->n_pad;
+  VtI8Args a{};
+  a.Aimg = Aimg;
+  a.Bimg = static_cast<const int8_t*>(h->Bimg.p);
+  a.nkb = (int)(np / 64);
+  a.nb2 = (int)(np / gpoz::TN);
+  a.b_mt = 0;
+  a.b_p = gpoz::B_SLICE;
+  a.b_k = (long)gpoz::S * gpoz::B_SLICE;
+  a.b_j = (long)a.nkb * a.b_k;
+  a.sB = h->sBv.d();
+  a.sA = kstar_scale(h);
+  a.ld_out = np;
+  a.m_pad = m_pad;
+  a.n_items = (int)(m_pad / gpoz::TM) * ((a.nb2 + 1) / 2);
+  a.out = Vt;
+  a.dig = Vimg;
+  a.nkb_out = a.nkb;
+  a.dig_mul = gpoz::DIGIT_MUL / v_scale(h);
+  a.sumsq = sumsq;
+  return launch_i8<OUT, false>(h, a, (double)m_pad * (double)np * (double)(np + 64));
+}
+
+// Gram[tile] (128 x 128, compact) = V_tile V_tile^T from the digit image of V: the two 64-row halves of the
+// tile's own A image are the B operand.  sV1 = device vector of >= 128 copies of v_scale.
+int launch_gram_i8(gpc_handle h, const int8_t* Vimg, long m_pad, const double* sV1, double* gram) {
+  const long np = h->n_pad;
+  VtI8Args a{};
+  a.Aimg = Vimg;
+  a.Bimg = Vimg;
+  a.nkb = (int)(np / 64);
+  a.nb2 = 2;
+  a.b_p = gpoz::A_SLICE;
+  a.b_k = (long)gpoz::S * gpoz::A_SLICE;
+  a.b_mt = (long)a.nkb * a.b_k;
+  a.b_j = gpoz::B_SLICE;
+  a.sB = sV1;
+  a.sA = v_scale(h);
+  a.ld_out = 128;
+  a.m_pad = m_pad;
+  a.n_items = (int)(m_pad / gpoz::TM) * 2;
+  a.out = gram;
+  return launch_i8<OUT_F64, true>(h, a, (double)m_pad * 128.0 * (double)np);
+}
+
+// P [m_pad][ldp] = V Vg^T from the digit images of V (A layout) and of the rows of Vg (B layout, scales sBg).
+int launch_cross_i8(gpc_handle h, const int8_t* Vimg, long m_pad, const int8_t* Bg, const double* sBg, long g_pad,
+                    double* P) {
+  const long np = h->n_pad;
+  VtI8Args a{};
+  a.Aimg = Vimg;
+  a.Bimg = Bg;
+  a.nkb = (int)(np / 64);
+  a.nb2 = (int)(g_pad / 64);
+  a.b_mt = 0;
+  a.b_p = gpoz::B_SLICE;
+  a.b_k = (long)gpoz::S * gpoz::B_SLICE;
+  a.b_j = (long)a.nkb * a.b_k;
+  a.sB = sBg;
+  a.sA = v_scale(h);
+  a.ld_out = g_pad;
+  a.m_pad = m_pad;
+  a.n_items = (int)(m_pad / gpoz::TM) * a.nb2;
+  a.out = P;
+  return launch_i8<OUT_F64, true>(h, a, (double)m_pad * (double)g_pad * (double)np);
 }
 
 // Posterior mean + variance of M device-resident test rows on the tcgen05 path, software-pipelined
@@ -418,7 +495,7 @@ int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean,
     CKL();
     CK(cudaEventRecord(h->ev_k[b], s2));
     CK(cudaStreamWaitEvent(s1, h->ev_k[b], 0));
-    if ((rc = launch_vt_i8<false, true>(h, static_cast<const int8_t*>(Ab[b]->p), m_pad, nullptr, h->sumsq.d()))) return rc;
+    if ((rc = launch_vt_i8<OUT_SUMSQ>(h, static_cast<const int8_t*>(Ab[b]->p), m_pad, nullptr, h->sumsq.d()))) return rc;
     k_finalize_pred<<<(unsigned)((m + 255) / 256), 256, 0, s1>>>(
         h->hyp, xs, m, m_pad, Mb[b]->d(), nchunks, h->sumsq.d(), 2 * h->nb, Gb[b]->d(),
         d_sx ? d_sx + (sx_rows == 1 ? 0 : o * 3) : nullptr, sx_rows, dmean ? dmean + o : nullptr, dvar + o, flags);
@@ -539,7 +616,7 @@ int gpc_destroy(gpc_handle h) {
   if (!h) return GPC_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
+  DevBuf* bufs[] = {&h->Vimg, &h->gBimg, &h->gsB, &h->sV1, &h->Pt, &h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
                     &h->status, &h->Wm, &h->gpart, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
                     &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->Aimg2, &h->meanpart2, &h->gradpart2, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};

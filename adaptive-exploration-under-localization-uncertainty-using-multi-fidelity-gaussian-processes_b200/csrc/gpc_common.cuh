@@ -50,6 +50,82 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- exp(-q), q >= 0 ----------------------------------------------------------------------------
+// exp(-q) for q >= 0, branch-free so that the eight columns a thread works on interleave in the FP64
+// pipe (the library exp() carries special-case branches that serialise them): k = rint(-q log2 e) by the
+// magic-number add, two-step Cody-Waite reduction to |r| <= ln2 / 2, degree-13 Taylor polynomial
+// (truncation 1.7e-16 relative at the interval edge), 2^k by an exponent-field add.  q is clamped at 700
+// (e^-700 = 1e-304 is zero against any digit or mean), so k >= -1010 and the result stays normal.
+__device__ __forceinline__ double gpc_exp_neg(double q) {
+  q = fmin(q, 700.0);
+  const double t = fma(q, -1.4426950408889634074, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -6.93147180369123816490e-01, -q);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;            // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// exp(-q[u]) for W independent arguments, written stage by stage so that the W dependency chains
+// advance together (W-way ILP in the FP64 pipe from a single warp; the library exp() carries
+// special-case branches that keep the columns of a thread from interleaving).  The stages are volatile
+// asm so that the compiler keeps them breadth-first instead of re-serialising the chains.
+__device__ __forceinline__ double fma_pinned(double a, double b, double c) {
+  double d;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+  return d;
+}
+
+template <int W>
+__device__ __forceinline__ void gpc_exp_neg_w(const double* __restrict__ qin, double* __restrict__ e) {
+  double q[W], t[W], r[W], p[W];
+#pragma unroll
+  for (int u = 0; u < W; ++u) q[u] = fmin(qin[u], 700.0);
+#pragma unroll
+  for (int u = 0; u < W; ++u) t[u] = fma_pinned(q[u], -1.4426950408889634074, 6755399441055744.0);
+#pragma unroll
+  for (int u = 0; u < W; ++u) r[u] = t[u] - 6755399441055744.0;       // kf
+#pragma unroll
+  for (int u = 0; u < W; ++u) q[u] = fma_pinned(r[u], -6.93147180369123816490e-01, -q[u]);
+#pragma unroll
+  for (int u = 0; u < W; ++u) r[u] = fma_pinned(r[u], -1.90821492927058770002e-10, q[u]);
+#pragma unroll
+  for (int u = 0; u < W; ++u) p[u] = fma_pinned(1.6059043836821613e-10, r[u], 2.08767569878681e-09);   // 1/13!, 1/12!
+#define GPC_EXP_STAGE(c)            \
+  _Pragma("unroll") for (int u = 0; u < W; ++u) p[u] = fma_pinned(p[u], r[u], c);
+  GPC_EXP_STAGE(2.505210838544172e-08)    // 1/11!
+  GPC_EXP_STAGE(2.755731922398589e-07)    // 1/10!
+  GPC_EXP_STAGE(2.7557319223985893e-06)   // 1/9!
+  GPC_EXP_STAGE(2.48015873015873e-05)     // 1/8!
+  GPC_EXP_STAGE(1.984126984126984e-04)    // 1/7!
+  GPC_EXP_STAGE(1.3888888888888889e-03)   // 1/6!
+  GPC_EXP_STAGE(8.333333333333333e-03)    // 1/5!
+  GPC_EXP_STAGE(4.1666666666666664e-02)   // 1/4!
+  GPC_EXP_STAGE(1.6666666666666666e-01)   // 1/3!
+  GPC_EXP_STAGE(0.5)
+  GPC_EXP_STAGE(1.0)
+  GPC_EXP_STAGE(1.0)
+#undef GPC_EXP_STAGE
+#pragma unroll
+  for (int u = 0; u < W; ++u)
+    e[u] = __hiloint2double(__double2hiint(p[u]) + (__double2loint(t[u]) << 20), __double2loint(p[u]));
+}
+
+
 // ---- mbarrier / bulk-copy (TMA) helpers ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -66,6 +66,27 @@ __global__ void __launch_bounds__(gpcg::NTHREADS, 1) k_cross_cov(const __grid_co
   }
 }
 
+__global__ void k_fill(double* __restrict__ x, int n, double v) {
+  if ((int)threadIdx.x < n) x[threadIdx.x] = v;
+}
+
+// INT8 path: the contraction P = V_c V_g^T comes from the tcgen05 kernel (digit images of V); this finishes
+// Bt[r][j] = k(row r, grid j) - P[r][j] in place (zero for invalid candidate rows and j >= G).
+__global__ void __launch_bounds__(256) k_cross_fin(const __grid_constant__ GpcHyp h, const double* __restrict__ Xr4,
+                                                   const double* __restrict__ Xg4, long G, long g_pad, long m_pad,
+                                                   double* __restrict__ Bt) {
+  const long total = m_pad * g_pad;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx / g_pad, j = idx - r * g_pad;
+    const double af = Xr4[r * 4 + 3];
+    double o = 0.0;
+    if (af >= 0.0 && j < G)
+      o = gpc_kval(h, Xr4[r * 4], Xr4[r * 4 + 1], Xr4[r * 4 + 2], af, Xg4[j * 4], Xg4[j * 4 + 1], Xg4[j * 4 + 2],
+                   Xg4[j * 4 + 3]) - Bt[idx];
+    Bt[idx] = o;
+  }
+}
+
 // ---- per-candidate small-matrix helpers (shared memory, leading dimension 65) ----------------
 #define GPC_IG_LD 65
 // dynamic shared memory of the per-candidate kernels: two k x k matrices, the span's points, scratch

@@ -151,17 +151,20 @@ __device__ __forceinline__ uint2 pack_slice8(const unsigned long long (&u)[8], i
 
 // ------------------------------------------------------------------------------------------
 // Digits of the rows of X = L^-1 (lower triangular, row-major, ld).  Row i is scaled by
-// sB[i] = 2^e with |X(i, :)| / sB[i] <= 1/2.  One warp per row; grid = n_pad / 8, 256 threads.
+// sB[i] = 2^e with |X(i, :)| / sB[i] <= 1/4.  One warp per row; grid = nrows / 8, 256 threads.  tri = 0: general rows
+// (the grid's V for the cross products of the information gain).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X, long ld, long n_pad,
-                                                    int8_t* __restrict__ Bimg, double* __restrict__ sB) {
+                                                    int8_t* __restrict__ Bimg, double* __restrict__ sB, long nrows,
+                                                    int tri) {
   using namespace gpoz;
   const long i = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (i >= n_pad) return;
+  if (i >= nrows) return;
   const double* row = X + i * ld;
+  const long klast = tri ? i : n_pad - 1;      // tri: lower-triangular operand, k-blocks beyond the diagonal stay zero
   double mx = 0.0;
-  for (long k = lane; k <= i; k += 32) mx = fmax(mx, fabs(row[k]));
+  for (long k = lane; k <= klast; k += 32) mx = fmax(mx, fabs(row[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   int e = 0;
@@ -171,14 +174,14 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   const double mul = DIGIT_MUL / scale;
   const long jb = i >> 6, r = i & 63;
   const long nkb = n_pad >> 6;
-  // every 16-byte chunk (16 consecutive k) of every slice; k-blocks beyond the diagonal stay zero
-  for (long c = lane; c < (jb + 1) * 4; c += 32) {
+  // every 16-byte chunk (16 consecutive k) of every slice
+  for (long c = lane; c < ((klast >> 6) + 1) * 4; c += 32) {
     const long kb = c >> 2, cc = c & 3;
     unsigned long long uu[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const long k = kb * 64 + cc * 16 + u;
-      const double x = (k <= i) ? row[k] : 0.0;
+      const double x = (k <= klast) ? row[k] : 0.0;
       uu[u] = (unsigned long long)(__double2ll_rn(x * mul) + DIGIT_BIAS);
     }
     int8_t* base = Bimg + ((jb * nkb + kb) * S) * (long)B_SLICE + (r >> 3) * 512 + cc * 128 + (r & 7) * 16;
@@ -186,81 +189,6 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
     for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(base + (long)p * B_SLICE) = pack_slice(uu, p);
   }
 }
-
-// exp(-q) for q >= 0, branch-free so that the eight columns a thread works on interleave in the FP64
-// pipe (the library exp() carries special-case branches that serialise them): k = rint(-q log2 e) by the
-// magic-number add, two-step Cody-Waite reduction to |r| <= ln2 / 2, degree-13 Taylor polynomial
-// (truncation 1.7e-16 relative at the interval edge), 2^k by an exponent-field add.  q is clamped at 700
-// (e^-700 = 1e-304 is zero against any digit or mean), so k >= -1010 and the result stays normal.
-__device__ __forceinline__ double gpc_exp_neg(double q) {
-  q = fmin(q, 700.0);
-  const double t = fma(q, -1.4426950408889634074, 6755399441055744.0);
-  const int k = __double2loint(t);
-  const double kf = t - 6755399441055744.0;
-  double r = fma(kf, -6.93147180369123816490e-01, -q);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;            // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);          // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);         // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);         // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);          // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);         // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);         // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-
-// exp(-q[u]) for W independent arguments, written stage by stage so that the W dependency chains
-// advance together (W-way ILP in the FP64 pipe from a single warp; the library exp() carries
-// special-case branches that keep the columns of a thread from interleaving).  The stages are volatile
-// asm so that the compiler keeps them breadth-first instead of re-serialising the chains.
-__device__ __forceinline__ double fma_pinned(double a, double b, double c) {
-  double d;
-  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
-  return d;
-}
-
-template <int W>
-__device__ __forceinline__ void gpc_exp_neg_w(const double* __restrict__ qin, double* __restrict__ e) {
-  double q[W], t[W], r[W], p[W];
-#pragma unroll
-  for (int u = 0; u < W; ++u) q[u] = fmin(qin[u], 700.0);
-#pragma unroll
-  for (int u = 0; u < W; ++u) t[u] = fma_pinned(q[u], -1.4426950408889634074, 6755399441055744.0);
-#pragma unroll
-  for (int u = 0; u < W; ++u) r[u] = t[u] - 6755399441055744.0;       // kf
-#pragma unroll
-  for (int u = 0; u < W; ++u) q[u] = fma_pinned(r[u], -6.93147180369123816490e-01, -q[u]);
-#pragma unroll
-  for (int u = 0; u < W; ++u) r[u] = fma_pinned(r[u], -1.90821492927058770002e-10, q[u]);
-#pragma unroll
-  for (int u = 0; u < W; ++u) p[u] = fma_pinned(1.6059043836821613e-10, r[u], 2.08767569878681e-09);   // 1/13!, 1/12!
-#define GPC_EXP_STAGE(c)            \
-  _Pragma("unroll") for (int u = 0; u < W; ++u) p[u] = fma_pinned(p[u], r[u], c);
-  GPC_EXP_STAGE(2.505210838544172e-08)    // 1/11!
-  GPC_EXP_STAGE(2.755731922398589e-07)    // 1/10!
-  GPC_EXP_STAGE(2.7557319223985893e-06)   // 1/9!
-  GPC_EXP_STAGE(2.48015873015873e-05)     // 1/8!
-  GPC_EXP_STAGE(1.984126984126984e-04)    // 1/7!
-  GPC_EXP_STAGE(1.3888888888888889e-03)   // 1/6!
-  GPC_EXP_STAGE(8.333333333333333e-03)    // 1/5!
-  GPC_EXP_STAGE(4.1666666666666664e-02)   // 1/4!
-  GPC_EXP_STAGE(1.6666666666666666e-01)   // 1/3!
-  GPC_EXP_STAGE(0.5)
-  GPC_EXP_STAGE(1.0)
-  GPC_EXP_STAGE(1.0)
-#undef GPC_EXP_STAGE
-#pragma unroll
-  for (int u = 0; u < W; ++u)
-    e[u] = __hiloint2double(__double2hiint(p[u]) + (__double2loint(t[u]) << 20), __double2loint(p[u]));
-}
-
 
 // Byte B of four 48-bit values -> 4 digit bytes of one slice.
 template <int B>
@@ -423,13 +351,55 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
 
 // ------------------------------------------------------------------------------------------
 // The contraction.  grid = min(#SMs, items), 192 threads, dynamic smem gpoz::SMEM_BYTES.
-//   sumsq [nb2][m_pad] (SUMSQ) / Vt [m_pad][ld] (STORE_V), as k_vt.
+//   D(test tile mt, B row tile jb) = sum_kb A[mt][kb] B[jb][kb]^T  as 21 exact digit GEMMs.
+// Schedules:  triangular (FULLK = false): item (mt, p) = B tiles nb2-1-p then p, k-blocks 0..jb (V = K* X^T with
+//             X = L^-1 lower triangular; every item has nb2 + 1 k-steps);
+//             full (FULLK = true): item (mt, jb), k-blocks 0..nkb-1 (Gram and cross products of V).
+// Outputs:    OUT_SUMSQ   sumsq[jb][m_pad] = sum_i D(n, i)^2 per test row (posterior variance);
+//             OUT_F64     out[n * ld_out + jb 64 + c] = D                       (full covariance / information gain);
+//             OUT_DIGITS  the digit image of D in the A-image layout (scale 2^48 / dig_mul), so that V itself can
+//                         be the operand of the next INT8 product without ever existing in FP64 in HBM.
+// B addressing is generic (byte strides per test tile / row tile / k-block / digit slice): the standard image
+// [jb][kb][S][4 KB] arrives as one 24 KB bulk copy per stage; for self products (Gram of a V tile) the two
+// 64-row halves of the A image of the SAME tile serve as B (six 4 KB copies per stage).
 // ------------------------------------------------------------------------------------------
-template <bool STORE_V, bool SUMSQ>
-__global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict__ Aimg, const int8_t* __restrict__ Bimg,
-                                                      const double* __restrict__ sB, double sA, long ld, int nb2,
-                                                      long m_pad, int n_items, double* __restrict__ Vt,
-                                                      double* __restrict__ sumsq) {
+enum { OUT_SUMSQ = 0, OUT_F64 = 1, OUT_DIGITS = 2 };
+
+struct VtI8Args {
+  const int8_t* Aimg;
+  const int8_t* Bimg;
+  long b_mt, b_j, b_k, b_p;   // byte strides of the B operand
+  const double* sB;           // scale of every B row
+  double sA;                  // scale of A
+  int nkb;                    // k-blocks (of 64) in the A image
+  int nb2;                    // B row tiles (of 64)
+  long ld_out, m_pad;
+  int n_items;
+  double* out;                // OUT_F64
+  int8_t* dig;                // OUT_DIGITS: [m_pad / 128][nkb_out][S][8 KB]
+  int nkb_out;
+  double dig_mul;             // 2^48 / (scale of the emitted digits)
+  double* sumsq;              // OUT_SUMSQ
+};
+
+template <bool FULLK>
+__device__ __forceinline__ void vt_item(int item, int nb2, int npair, int& mt, int (&jbs)[2], int& nseg) {
+  if (FULLK) {
+    mt = item / nb2;
+    jbs[0] = item - mt * nb2;
+    jbs[1] = 0;
+    nseg = 1;
+  } else {
+    mt = item / npair;
+    const int p = item - mt * npair;
+    jbs[0] = nb2 - 1 - p;
+    jbs[1] = p;
+    nseg = (jbs[1] < jbs[0]) ? 2 : 1;
+  }
+}
+
+template <int OUT, bool FULLK>
+__global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ VtI8Args a) {
   using namespace gpoz;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -437,8 +407,12 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
   __shared__ uint32_t tmem_base_s;
   __shared__ double sb_tile[2][TN];   // row scales of the tile being drained (x 2^-56 sA), double-buffered
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb2 = a.nb2, n_items = a.n_items;
   const int npair = (nb2 + 1) / 2;
-  const long nkb_total = ld >> 6;
+  const long nkb_total = a.nkb;
+  const long m_pad = a.m_pad;
+  const double sA = a.sA;
+  const double* __restrict__ sB = a.sB;
 
   if (tid == 0) {
 #pragma unroll
@@ -462,18 +436,24 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
     if (lane == 0) {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mt = item / npair, p = item - mt * npair;
-        const int jbs[2] = {nb2 - 1 - p, p};
-        const int nseg = (jbs[1] < jbs[0]) ? 2 : 1;
+        int mt, jbs[2], nseg;
+        vt_item<FULLK>(item, nb2, npair, mt, jbs, nseg);
         for (int sg = 0; sg < nseg; ++sg) {
           const int jb = jbs[sg];
-          for (int kb = 0; kb <= jb; ++kb, ++it) {
+          const int kend = FULLK ? (int)nkb_total : jb + 1;
+          for (int kb = 0; kb < kend; ++kb, ++it) {
             const int st = it % STAGES;
             if (it >= STAGES) mbar_wait_guarded(&empty_bar[st], ((it / STAGES) - 1) & 1);
             uint8_t* dst = smem + st * STAGE_BYTES;
             mbar_expect_tx(&full_bar[st], STAGE_BYTES);
-            tma_bulk_g2s(dst, Aimg + (((long)mt * nkb_total + kb) * S) * (long)A_SLICE, A_STAGE, &full_bar[st]);
-            tma_bulk_g2s(dst + A_STAGE, Bimg + (((long)jb * nkb_total + kb) * S) * (long)B_SLICE, B_STAGE, &full_bar[st]);
+            tma_bulk_g2s(dst, a.Aimg + (((long)mt * nkb_total + kb) * S) * (long)A_SLICE, A_STAGE, &full_bar[st]);
+            const int8_t* bsrc = a.Bimg + (long)mt * a.b_mt + (long)jb * a.b_j + (long)kb * a.b_k;
+            if (a.b_p == (long)B_SLICE) {
+              tma_bulk_g2s(dst + A_STAGE, bsrc, B_STAGE, &full_bar[st]);
+            } else {
+#pragma unroll
+              for (int p = 0; p < S; ++p) tma_bulk_g2s(dst + A_STAGE + p * B_SLICE, bsrc + (long)p * a.b_p, B_SLICE, &full_bar[st]);
+            }
           }
         }
       }
@@ -485,15 +465,15 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
       const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);
       uint32_t it = 0, tile = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mt = item / npair, p = item - mt * npair;
+        int mt, jbs[2], nseg;
+        vt_item<FULLK>(item, nb2, npair, mt, jbs, nseg);
         (void)mt;
-        const int jbs[2] = {nb2 - 1 - p, p};
-        const int nseg = (jbs[1] < jbs[0]) ? 2 : 1;
         for (int sg = 0; sg < nseg; ++sg, ++tile) {
           const int jb = jbs[sg];
+          const int kend = FULLK ? (int)nkb_total : jb + 1;
           if (tile > 0) mbar_wait_guarded(&tmem_empty_bar, (tile - 1) & 1);  // epilogue drained the accumulators
           asm volatile("tcgen05.fence::after_thread_sync;");
-          for (int kb = 0; kb <= jb; ++kb, ++it) {
+          for (int kb = 0; kb < kend; ++kb, ++it) {
             const int st = it % STAGES;
             mbar_wait_guarded(&full_bar[st], (it / STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
@@ -536,9 +516,8 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
     const double cs = COMB_SCALE * sA;
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mt = item / npair, p = item - mt * npair;
-      const int jbs[2] = {nb2 - 1 - p, p};
-      const int nseg = (jbs[1] < jbs[0]) ? 2 : 1;
+      int mt, jbs[2], nseg;
+      vt_item<FULLK>(item, nb2, npair, mt, jbs, nseg);
       for (int sg = 0; sg < nseg; ++sg, ++tile) {
         const int jb = jbs[sg];
         double* sbt = sb_tile[tile & 1];
@@ -581,13 +560,26 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const int8_t* __restrict_
             vv[j] = comb * sbt[c0 + j];
             ss = fma(vv[j], vv[j], ss);
           }
-          if (STORE_V) {
-            double* dst = Vt + n * ld + (long)jb * TN + c0;
+          if (OUT == OUT_F64) {
+            double* dst = a.out + n * a.ld_out + (long)jb * TN + c0;
 #pragma unroll
             for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(vv[j], vv[j + 1]);
           }
+          if (OUT == OUT_DIGITS) {
+            unsigned long long dv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dv[j] = (unsigned long long)(__double2ll_rn(vv[j] * a.dig_mul) + DIGIT_BIAS);
+            int8_t* dst = a.dig + (((long)mt * a.nkb_out + jb) * S) * (long)A_SLICE + (row >> 3) * 512 + (c0 >> 4) * 128 +
+                          (row & 7) * 16 + (c0 & 15);
+            *reinterpret_cast<uint2*>(dst + 0L * A_SLICE) = pack_bytes8<5>(dv);
+            *reinterpret_cast<uint2*>(dst + 1L * A_SLICE) = pack_bytes8<4>(dv);
+            *reinterpret_cast<uint2*>(dst + 2L * A_SLICE) = pack_bytes8<3>(dv);
+            *reinterpret_cast<uint2*>(dst + 3L * A_SLICE) = pack_bytes8<2>(dv);
+            *reinterpret_cast<uint2*>(dst + 4L * A_SLICE) = pack_bytes8<1>(dv);
+            *reinterpret_cast<uint2*>(dst + 5L * A_SLICE) = pack_bytes8<0>(dv);
+          }
         }
-        if (SUMSQ) sumsq[(long)jb * m_pad + n] = ss;
+        if (OUT == OUT_SUMSQ) a.sumsq[(long)jb * m_pad + n] = ss;
       }
     }
   }

@@ -118,19 +118,23 @@ __global__ void __launch_bounds__(256) k_kstar(const __grid_constant__ GpcHyp h,
 #pragma unroll 1
       for (int m = 0; m <= mm; ++m) {
         const double c0 = hil[m][0], c1 = hil[m][1], c2 = hil[m][2];
+        double q[4], e[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const double sx = dx[u] * c0, sy = dy[u] * c1, sz = dz[u] * c2;
-          const double q = fma(sx, sx, fma(sy, sy, sz * sz));
-          double e;
-          if (base == 0) {
-            e = exp(-q);
-          } else {
-            const double rt = 1.7320508075688772 * sqrt(q);
-            e = (1.0 + rt) * exp(-rt);
-          }
-          kv[u] = fma(cw[warp][m][fj[u]], e, kv[u]);
+          q[u] = fma(sx, sx, fma(sy, sy, sz * sz));
         }
+        if (base == 0) {
+          gpc_exp_neg_w<4>(q, e);      // branch-free, the four columns of the lane advance together
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) q[u] = 1.7320508075688772 * sqrt(q[u]);
+          gpc_exp_neg_w<4>(q, e);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) e[u] *= 1.0 + q[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kv[u] = fma(cw[warp][m][fj[u]], e[u], kv[u]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

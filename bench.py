@@ -507,6 +507,22 @@ def run_ours(args):
         except Exception as exc:   # context only
             other = {"error": str(exc)}
 
+    # ---- posterior MEAN only (K* alpha fused into the covariance assembly, no contraction): context for the
+    # north_star's 1e9 points/s figure, which is a mean-only / FP64-ALU-bound rate -----------------
+    mean_only = None
+    if dist is None:
+        def step_mean():
+            core.predict_dev(dXs.data_ptr(), M, dmean.data_ptr(), 0, flags | L.MEAN_ONLY)
+        for _ in range(2):
+            step_mean()
+        torch.cuda.synchronize()
+        mms = timed(step_mean, 3, 0)
+        terms = 1.0 if nigp_mode else 1.2      # AR1 terms per (test, train) pair of this workload
+        mean_only = {"value": M * 3 / (mms * 1e-3), "unit": "pts/s", "ms_per_step": mms / 3,
+                     "kernel_evals_per_s": M * 3 * float(N) * terms / (mms * 1e-3),
+                     "exp_peak_per_s": 784e9, "note": "N kernel evaluations + 2N flop per point; library exp(double) "
+                     "peaks at 784 G/s on this B200 (profiles/microbench/fp64_peaks_r01.txt)"}
+
     # ---- the factorisation (once per hyper-parameter / data change): assembly + Cholesky + explicit L^-1 +
     # alpha + log-det, warm buffers, best of 3 -------------------------------------------------------------
     factor = None
@@ -542,7 +558,8 @@ def run_ours(args):
                     "api": api},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "mode": args.mode, "other_mode": other,
-            "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast, "factor": factor}
+            "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast, "factor": factor,
+            "mean_only": mean_only}
 
     if args.ig and not nigp_mode:
         line["ig"] = bench_ig(args, gpcore, L, torch, local)
@@ -563,7 +580,8 @@ def bench_ig(args, gpcore, L, torch, local):
     g = np.meshgrid(np.linspace(0, 10, 10), np.linspace(0, 20, 6), np.linspace(0, 10, 5))
     grid4 = np.ascontiguousarray(np.hstack([np.array([gi.ravel("F") for gi in g]).T, 2 * np.ones((300, 1))]))
     rows, offs = make_candidates(C, k, F)
-    core.ig_logdet(grid4, rows[:k * 256], offs[:257])     # warm-up (allocations)
+    core.ig_logdet(grid4, rows[:k * 1024], offs[:1025])   # warm-up: two full 16384-row chunks size every buffer
+    core.ig_seq(rows[:k * 1024], offs[:1025], MF3_PARAMS[-1], pred_fid=0)
     torch.cuda.synchronize()
     core.enable_hot_timing(True)
     core.hot_kernel_time(reset=True)
@@ -578,7 +596,7 @@ def bench_ig(args, gpcore, L, torch, local):
     # calculatePathInfoEmuBatch as the reference computes it (emukit's element-wise 1e-10 clip of both G x G
     # covariances: one 300 x 300 factorisation per candidate instead of a k x k update), on a bounded subset
     Cc = min(C, 8192)
-    core.ig_logdet(grid4, rows[:k * 256], offs[:257], clip=True)
+    core.ig_logdet(grid4, rows[:k * 1024], offs[:1025], clip=True)
     t0 = time.perf_counter()
     Ic, _, _ = core.ig_logdet(grid4, rows[:k * Cc], offs[:Cc + 1], clip=True)
     dt_clip = time.perf_counter() - t0

@@ -1,5 +1,5 @@
 """Condense `ncu -i X.ncu-rep --page raw --csv` output to the metrics the profiles/ summaries quote.
-usage: ncu -i X.ncu-rep --page raw --csv | python profiles/ncu_summary.py > profiles/rNN/ncu_<kernel>.csv"""
+usage: ncu -i X.ncu-rep --page raw --csv | python profiles/tools/ncu_summary.py > profiles/rNN/ncu_<kernel>.csv"""
 import csv
 import sys
 

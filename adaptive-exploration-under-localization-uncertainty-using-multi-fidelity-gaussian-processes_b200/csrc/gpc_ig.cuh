@@ -370,26 +370,35 @@ __global__ void __launch_bounds__(128) k_ig_selfgrid_cand(const __grid_constant_
 //   out[c] = ldp ? 0.5 (*ldp - logdet) : logdet      (spans == NULL: one evaluation with k = 0 = the prior)
 // ------------------------------------------------------------------------------------------
 constexpr int GPC_CLIP_NB = 32;
-constexpr int GPC_CLIP_FIXED = GPC_MAXK * GPC_IG_LD + GPC_MAXK * 4 + 2 * GPC_CLIP_NB * (GPC_CLIP_NB + 1) + 18;  // doubles
-inline size_t ig_clip_smem(int kcap, int GP) { return ((size_t)GPC_CLIP_FIXED + (size_t)kcap * GP) * 8; }
+// shared memory (doubles): [S (kcap x 65) -- reused for D and Lp (2 x 32 x 33) once W^T is formed][points kcap x 4]
+// [scratch 18 + 32 reciprocal pivots][W^T kcap x GP].  Two CTAs fit per SM for k <= 32, G <= 320: while one CTA is in
+// the one-warp diagonal-block factorisation the other keeps the FP64 pipe busy.
+inline int ig_clip_head(int kcap) {
+  const int a = kcap * GPC_IG_LD, b = 2 * GPC_CLIP_NB * (GPC_CLIP_NB + 1);
+  return (a > b ? a : b) + kcap * 4 + 18 + GPC_CLIP_NB;
+}
+inline size_t ig_clip_smem(int kcap, int GP) { return ((size_t)ig_clip_head(kcap) + (size_t)kcap * GP) * 8; }
 
-__global__ void __launch_bounds__(256, 1) k_ig_logdet_clip(const __grid_constant__ GpcHyp h,
+__global__ void __launch_bounds__(256, 2) k_ig_logdet_clip(const __grid_constant__ GpcHyp h,
                                                            const GpcSpan* __restrict__ spans, int ncand,
                                                            const double* __restrict__ Xr4,
                                                            const double* __restrict__ Gram,
                                                            const double* __restrict__ Bt, long ldb,
                                                            const double* __restrict__ S0, long lds, int G, int GP,
                                                            double* scratch, double clip_lo,
-                                                           const double* __restrict__ ldp, double* __restrict__ out) {
+                                                           const double* __restrict__ ldp, double* __restrict__ out,
+                                                           int kcap) {
   extern __shared__ double dsm[];
   constexpr int NB = GPC_CLIP_NB, LDD = GPC_CLIP_NB + 1;
-  double* S = dsm;
-  double(*pt)[4] = reinterpret_cast<double(*)[4]>(S + GPC_MAXK * GPC_IG_LD);
-  double* D = S + GPC_MAXK * GPC_IG_LD + GPC_MAXK * 4;
+  const int sdim = (kcap * GPC_IG_LD > 2 * NB * LDD) ? kcap * GPC_IG_LD : 2 * NB * LDD;
+  double* S = dsm;                 // candidate covariance, dead once W^T exists ...
+  double* D = dsm;                 // ... then the diagonal block and the staged multipliers live there
   double* Lp = D + NB * LDD;
-  double* red = Lp + NB * LDD;
+  double(*pt)[4] = reinterpret_cast<double(*)[4]>(dsm + sdim);
+  double* red = dsm + sdim + kcap * 4;
   int* flagp = reinterpret_cast<int*>(red + 16);
-  double* Wt = red + 18;
+  double* rdiag = red + 18;        // reciprocal pivots of the current diagonal block
+  double* Wt = rdiag + NB;
   double* Lt = scratch + (size_t)blockIdx.x * GP * GP;   // Lt[j * GP + i] = L[i][j]
   const int tid = threadIdx.x;
   for (int c = blockIdx.x; c < ncand; c += gridDim.x) {
@@ -458,11 +467,18 @@ __global__ void __launch_bounds__(256, 1) k_ig_logdet_clip(const __grid_constant
           for (int e = tid; e < NB * NB; e += blockDim.x) Lp[(e >> 5) * LDD + (e & 31)] = Lt[(size_t)(j0 + (e >> 5)) * GP + p0 + (e & 31)];
           __syncthreads();
           if (act) {
-#pragma unroll 4
-            for (int jj = 0; jj < NB; ++jj) {
-              const double a = Lt[(size_t)(j0 + jj) * GP + i];
+            // the multipliers of this row come out of the L2-resident scratch: fetch eight at a time so that
+            // their latency overlaps (one load followed by its 32 FMAs would expose it every iteration)
+#pragma unroll 1
+            for (int j8 = 0; j8 < NB; j8 += 8) {
+              double av[8];
 #pragma unroll
-              for (int cc = 0; cc < NB; ++cc) acc[cc] = fma(-a, Lp[jj * LDD + cc], acc[cc]);
+              for (int u = 0; u < 8; ++u) av[u] = Lt[(size_t)(j0 + j8 + u) * GP + i];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) acc[cc] = fma(-av[u], Lp[(j8 + u) * LDD + cc], acc[cc]);
+              }
             }
           }
         }
@@ -490,6 +506,7 @@ __global__ void __launch_bounds__(256, 1) k_ig_logdet_clip(const __grid_constant
               __syncwarp();
             }
             ldsum += log(D[lane * LDD + lane]);
+            rdiag[lane] = 1.0 / D[lane * LDD + lane];
           }
           __syncthreads();
         }
@@ -500,7 +517,7 @@ __global__ void __launch_bounds__(256, 1) k_ig_logdet_clip(const __grid_constant
               double v = acc[cc];
 #pragma unroll
               for (int c2 = 0; c2 < cc; ++c2) v = fma(-acc[c2], D[cc * LDD + c2], v);
-              acc[cc] = v / D[cc * LDD + cc];
+              acc[cc] = v * rdiag[cc];
             }
 #pragma unroll
             for (int cc = 0; cc < NB; ++cc) Lt[(size_t)(p0 + cc) * GP + i] = acc[cc];

@@ -109,3 +109,41 @@ def test_int8_extreme_scales(gpcore_mod, go):
         m1, v1 = core.predict(Xs4, L_.INCLUDE_NOISE | L_.CLIP_DIAG)
         assert normwise(m1, mu[:, 0]) < 1e-8 and normwise(v1, var[:, 0], p[0]) < TOL, p
         core.close()
+
+
+@pytest.mark.parametrize("scale,noise", [(1.0, 1.0), (2500.0, 1e-3), (1e-3, 1.0)])
+def test_int8_information_gain_matches_fp64(gpcore_mod, go, scale, noise):
+    """The information-gain operators run end to end on the INT8 path (V emitted as a digit image, Gram and cross
+    products from it); the FP64 DMMA path of the same handle is the cross-check, the oracle's literal refit loop the
+    reference.  Kernel variances x scale and noise x noise exercise the fixed-point scale of V."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(31)
+    N, F = 600, 3
+    X4, y = synth(rng, N, F)
+    p = MF_PARAMS.copy()
+    p[[0, 4, 8]] *= scale
+    p[-3:] *= scale * noise
+    core = gpcore_mod.GPCore(L_.KIND_MF_AR1_RBF, F, 0)
+    core.set_hypers(p, 1e-8)
+    core.set_data(X4, y * np.sqrt(scale))
+    core.factor()
+    ks = [1, 7, 32, 0, 64, 19, 33]
+    cands = [np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (k, 3)), rng.integers(0, F, (k, 1)).astype(float)]) for k in ks]
+    cands[1][:, :3] = X4[:7, :3] + 1e-3                    # next to training points: Schur complements ~ noise
+    rows, offs = gpcore_mod.GPCore._ragged(cands)
+    grid = rng.uniform([0, 0, 0], [10, 20, 10], (150, 3))
+    g4 = np.hstack([grid, 2 * np.ones((150, 1))])
+    out = {}
+    for mode in (L_.MODE_FP64, L_.MODE_INT8):
+        core.set_mode(mode)
+        out[mode] = (core.ig_seq(rows, offs, float(p[-1]), pred_fid=0)[0], core.ig_logdet(g4, rows, offs)[0],
+                     core.ig_logdet(g4, rows, offs, clip=True)[0], core.ig_selfgrid(rows, offs, pred_fid=2, clip=True)[0])
+    # signal-to-noise 4e4 (scale 2500, noise 1e-3): cond(K) ~ 1e7 and the two paths -- both approximate there -- spread
+    # to a few 1e-9; the tolerance says so
+    tol = 2e-8 if noise < 1.0 else 1e-9
+    for a, b in zip(out[L_.MODE_FP64], out[L_.MODE_INT8]):
+        assert normwise(b, a, 1.0) < tol, (a, b)
+    ref = go.MFGP(X4, y * np.sqrt(scale), p, F=F, gram=False)
+    want = np.array([go.ig_logdet_refit(ref, g4, c) if len(c) else 0.0 for c in cands[:4]])
+    assert normwise(out[L_.MODE_INT8][1][:4], want, 1.0) < 1e-7
+    core.close()

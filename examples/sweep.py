@@ -39,6 +39,8 @@ def main():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG", None)     # keep stdout to the JSON lines (NCCL prints its version banner there)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)

@@ -12,6 +12,7 @@
 #include "gpc_factor.cuh"
 #include "gpc_grad.cuh"
 #include "gpc_ig.cuh"
+#include "gpc_gridmean.cuh"
 #include "gpc_ozaki.cuh"
 #include "gpc_predict.cuh"
 #include "gpc_traj.cuh"
@@ -74,6 +75,7 @@ struct gpc_handle_s {
   int n_sm = 0;
   // information-gain workspaces
   DevBuf gX4, gVt, gS, gSinv, gT, Bt, Zt, cand_off, cand_I, cand_aux, cand_rows, cand_mask, gram, gramZ;
+  DevBuf gmT, gmA, gmC, gmc, gmax, gmmean;   // tensor-grid mean: axis tables, A rows, C tile rows, coefficients, axes, result
   DevBuf Vimg, gBimg, gsB, sV1, Pt;   // INT8 information gain: digit images of V (candidates) and of the grid's V, scales
   // hot-kernel timing
   bool hot_timing = false;
@@ -124,6 +126,7 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_ig_logdet_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_ig_selfgrid_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
+  CK(cudaFuncSetAttribute(k_gm_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
@@ -616,7 +619,7 @@ int gpc_destroy(gpc_handle h) {
   if (!h) return GPC_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->Vimg, &h->gBimg, &h->gsB, &h->sV1, &h->Pt, &h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
+  DevBuf* bufs[] = {&h->gmT, &h->gmA, &h->gmC, &h->gmc, &h->gmax, &h->gmmean, &h->Vimg, &h->gBimg, &h->gsB, &h->sV1, &h->Pt, &h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
                     &h->status, &h->Wm, &h->gpart, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
                     &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->Aimg2, &h->meanpart2, &h->gradpart2, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
@@ -1001,6 +1004,79 @@ int gpc_predict_noisy(gpc_handle h, const double* Xs4, long M, const double* sx,
                       double* var, unsigned flags) {
   if (!sx) return fail(h, GPC_ERR_ARG, "sx == NULL");
   return predict_host(h, Xs4, M, sx, sx_rows, mean, var, flags);
+}
+
+// dmean != NULL: device output (asynchronous on the handle's stream), else the result is copied to `mean` (host).
+static int grid_mean_impl(gpc_handle h, const double* ax, long nx, const double* ay, long ny, const double* az, long nz,
+                          double fid, double* mean, double* dmean) {
+  int rc = require_factor(h);
+  if (rc) return rc;
+  if (!ax || !ay || !az || (!mean && !dmean) || nx < 1 || ny < 1 || nz < 1) return fail(h, GPC_ERR_SHAPE, "bad grid axes");
+  if (h->hyp.base != 0) return fail(h, GPC_ERR_ARG, "the tensor-grid mean needs a squared-exponential kernel (it separates per axis)");
+  if (h->F > 1 && ((int)fid < 0 || (int)fid >= h->F)) return fail(h, GPC_ERR_ARG, "fidelity index out of range");
+  if (nx > 65535 || ny > 65535 || nz > 65472) return fail(h, GPC_ERR_SHAPE, "an axis has more than 65535 points");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const long np = h->n_pad, npairs = nx * ny;
+  const long nzp = round_up(nz, 64), nxp = nx, nyp = ny;
+  const long R = std::min<long>(round_up(npairs, 64), 8192);          // (ix, iy) pairs per pass
+  const int fi = h->F > 1 ? (int)fid : 0;
+  CK(h->gmax.ensure((size_t)(nx + ny + nz) * 8));
+  CK(h->gmT.ensure((size_t)(nxp + nyp + nzp) * np * 8));
+  CK(h->gmA.ensure((size_t)R * np * 8));
+  CK(h->gmC.ensure((size_t)R * nzp * 8));
+  CK(h->gmc.ensure((size_t)np * 8));
+  if (!dmean) {
+    CK(h->gmmean.ensure((size_t)npairs * nz * 8));
+    dmean = h->gmmean.d();
+  }
+  double* dax = h->gmax.d();
+  double* day = dax + nx;
+  double* daz = day + ny;
+  CK(cudaMemcpyAsync(dax, ax, (size_t)nx * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(day, ay, (size_t)ny * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(daz, az, (size_t)nz * 8, cudaMemcpyHostToDevice, s));
+  double* Tx = h->gmT.d();
+  double* Ty = Tx + nxp * np;
+  double* Tz = Ty + nyp * np;
+  const int mtop = fi < h->F - 1 ? fi : h->F - 1;
+  const unsigned nb256 = (unsigned)((np + 255) / 256);
+  for (long p0 = 0; p0 < npairs; p0 += R) {
+    for (int m = 0; m <= mtop; ++m) {
+      if (p0 == 0 || mtop > 0) {   // one term: the tables are built once; several terms: per pass and term
+        k_gm_table<<<dim3(nb256, (unsigned)nxp), 256, 0, s>>>(h->hyp, h->Xt.d(), np, h->N, dax, (int)nx, 0, m, Tx);
+        k_gm_table<<<dim3(nb256, (unsigned)nyp), 256, 0, s>>>(h->hyp, h->Xt.d(), np, h->N, day, (int)ny, 1, m, Ty);
+        k_gm_table<<<dim3(nb256, (unsigned)nzp), 256, 0, s>>>(h->hyp, h->Xt.d(), np, h->N, daz, (int)nz, 2, m, Tz);
+        k_gm_coef<<<nb256, 256, 0, s>>>(h->hyp, h->Xt.d(), h->alpha.d(), np, h->N, fi, m, h->gmc.d());
+        CKL();
+        h->launches += 3;
+      }
+      k_gm_form<<<dim3(nb256, (unsigned)R), 256, 0, s>>>(h->gmc.d(), Tx, Ty, np, p0, npairs, (int)ny, h->gmA.d());
+      CKL();
+      k_gm_gemm<<<dim3((unsigned)(nzp / 64), (unsigned)(R / 64)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(
+          h->gmA.d(), Tz, np, h->gmC.d(), nzp, m == 0 ? 0.0 : 1.0);
+      CKL();
+    }
+    k_gm_store<<<(unsigned)(4 * h->n_sm), 256, 0, s>>>(h->gmC.d(), nzp, p0, npairs, (int)nz, R, dmean);
+    CKL();
+  }
+  if (mean) {
+    CK(cudaMemcpyAsync(mean, dmean, (size_t)npairs * nz * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return GPC_OK;
+}
+
+int gpc_predict_grid_mean(gpc_handle h, const double* ax, long nx, const double* ay, long ny, const double* az, long nz,
+                          double fid, double* mean) {
+  if (!mean) return fail(h, GPC_ERR_SHAPE, "mean is NULL");
+  return grid_mean_impl(h, ax, nx, ay, ny, az, nz, fid, mean, nullptr);
+}
+
+int gpc_predict_grid_mean_dev(gpc_handle h, const double* ax, long nx, const double* ay, long ny, const double* az,
+                              long nz, double fid, double* dmean) {
+  if (!dmean) return fail(h, GPC_ERR_SHAPE, "dmean is NULL");
+  return grid_mean_impl(h, ax, nx, ay, ny, az, nz, fid, nullptr, dmean);
 }
 
 int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, double* cov, const double* extra_diag,

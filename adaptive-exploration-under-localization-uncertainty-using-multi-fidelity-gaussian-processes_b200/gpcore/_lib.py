@@ -77,6 +77,8 @@ SIGNATURES = {
     "gpc_kernel_matrix": (C.c_int, [_h, _dp, C.c_long, _dp, C.c_long, _dp]),
     "gpc_predict": (C.c_int, [_h, _dp, C.c_long, _dp, _dp, C.c_uint]),
     "gpc_predict_dev": (C.c_int, [_h, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_uint]),
+    "gpc_predict_grid_mean": (C.c_int, [_h, _dp, C.c_long, _dp, C.c_long, _dp, C.c_long, C.c_double, _dp]),
+    "gpc_predict_grid_mean_dev": (C.c_int, [_h, _dp, C.c_long, _dp, C.c_long, _dp, C.c_long, C.c_double, C.c_void_p]),
     "gpc_predict_noisy": (C.c_int, [_h, _dp, C.c_long, _dp, C.c_long, _dp, _dp, C.c_uint]),
     "gpc_predict_cov": (C.c_int, [_h, _dp, C.c_long, _dp, _dp, _dp, C.c_uint]),
     "gpc_mean_grad": (C.c_int, [_h, _dp, C.c_long, _dp, _dp]),

@@ -222,6 +222,11 @@ class NIGP:
             self._stamp = stamp
         return self._gp
 
+    def predict_grid_mean(self, ax, ay, az):
+        """Extension: ``predict(grid, return_var=False)`` for the tensor grid ``np.meshgrid(ax, ay, az, indexing="ij")``
+        as FP64 tensor-core GEMMs; shape ``(len(ax), len(ay), len(az))``."""
+        return self._factor().predict_grid_mean(ax, ay, az, 0)
+
     def predict(self, Xs, Xs_input_noise=None, return_var=True, return_cov=False):
         """``NIGP.py:269-333``.  ``return_cov=False`` computes only the diagonal (the reference
         always builds the M x M matrix, ``:299``), with identical values."""

@@ -530,7 +530,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         mms = timed(step_mean, 3, 0)
         terms = 1.0 if nigp_mode else 1.2      # AR1 terms per (test, train) pair of this workload
-        mean_only = {"value": M * 3 / (mms * 1e-3), "unit": "pts/s", "ms_per_step": mms / 3,
+        terms_grid = 1.0 if nigp_mode else 2.0  # the grid path contracts every term over all training points
+        # the same mean on the benchmark's test set AS A TENSOR GRID (it is one): gpc_predict_grid_mean, device output
+        side = int(round(M ** (1.0 / 3)))
+        grid_line = None
+        if side ** 3 == M:
+            axs = [np.linspace(0.0, 10, side), np.linspace(0.0, 20, side), np.linspace(0.0, 10, side)]
+            gm = torch.empty(M, dtype=torch.float64, device="cuda")
+            core.predict_grid_mean_dev(axs[0], axs[1], axs[2], F - 1, gm.data_ptr())
+            torch.cuda.synchronize()
+            gms = timed(lambda: core.predict_grid_mean_dev(axs[0], axs[1], axs[2], F - 1, gm.data_ptr()), 3, 0)
+            grid_line = {"value": M * 3 / (gms * 1e-3), "unit": "pts/s", "ms_per_step": gms / 3,
+                         "dgemm_tflops": 2.0 * M * float(N) * terms_grid * 3 / (gms * 1e-3) / 1e12,
+                         "api": "gpc_predict_grid_mean_dev (separable cross-covariance, contraction over the training "
+                                "index as FP64 DMMA GEMMs)"}
+        mean_only = {"value": M * 3 / (mms * 1e-3), "unit": "pts/s", "ms_per_step": mms / 3, "tensor_grid": grid_line,
                      "kernel_evals_per_s": M * 3 * float(N) * terms / (mms * 1e-3),
                      "exp_peak_per_s": 784e9, "note": "N kernel evaluations + 2N flop per point; library exp(double) "
                      "peaks at 784 G/s on this B200 (profiles/microbench/fp64_peaks_r01.txt)"}

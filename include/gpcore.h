@@ -124,6 +124,16 @@ int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, dou
  * fused on the device; sx is (1 x 3) when sx_rows == 1, else (M x 3) input-noise std devs. */
 int gpc_predict_noisy(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows,
                       double* mean, double* var, unsigned flags);
+/* Posterior MEAN on a tensor grid (squared-exponential kernels only): grid point (i, j, k) = (ax[i], ay[j], az[k])
+ * at fidelity index fid, mean[(i * ny + j) * nz + k] -- np.meshgrid(ax, ay, az, indexing="ij") raveled in C order.
+ * Every test set of the reference is such a grid (exploreSimSettings.py:116-119, the planner's fieldGrid); the
+ * cross-covariance separates per axis, so the mean is (nx ny) x nz x N GEMMs on the FP64 tensor cores (2 M N flop)
+ * instead of M N kernel evaluations.  Same values as gpc_predict's mean to O(ulp) per product of three exps. */
+int gpc_predict_grid_mean(gpc_handle h, const double* ax, long nx, const double* ay, long ny, const double* az,
+                          long nz, double fid, double* mean);
+/* The same with a DEVICE output pointer (axes stay host arrays: they are tiny); asynchronous on gpc_stream(h). */
+int gpc_predict_grid_mean_dev(gpc_handle h, const double* ax, long nx, const double* ay, long ny, const double* az,
+                              long nz, double fid, double* dmean);
 /* Full M x M posterior covariance (GPy predict(full_cov=1), emukit predict_covariance,
  * NIGP.predict(return_cov=1)); mean may be NULL.  extra_diag (M, may be NULL) is added to the
  * diagonal (NIGP's test-input noise term, NIGP.py:321-324). */

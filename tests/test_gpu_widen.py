@@ -451,3 +451,64 @@ def test_getEID_on_device_models(gpcore_mod):
         assert np.max(np.abs(E - g["sf_auto%d" % auto])) < 1e-8 * np.max(g["sf_auto%d" % auto])
         E, _ = getEID(mf, g["WS"], float(g["mD"]), emu=True, auto=auto)
         assert np.max(np.abs(E - g["mf_auto%d" % auto])) < 1e-8 * np.max(g["mf_auto%d" % auto])
+
+
+def test_tensor_grid_mean_as_gemm(gpcore_mod, go):
+    """gpc_predict_grid_mean (separable squared-exponential cross-covariance, contraction over the training index as
+    FP64 tensor-core GEMMs) against the general predict on the materialised grid and against the oracle: single
+    fidelity, three-fidelity AR1 at every query fidelity, ragged axis lengths, several passes (> 8192 (ix, iy)
+    pairs); Matern is rejected."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(9)
+
+    def mesh(ax, ay, az, f):
+        g = np.meshgrid(ax, ay, az, indexing="ij")
+        P = np.stack([gi.ravel() for gi in g], 1)
+        return np.ascontiguousarray(np.hstack([P, np.full((len(P), 1), float(f))]))
+
+    for kind, F, p, N in ((L_.KIND_SF_RBF, 1, SF_PARAMS, 333), (L_.KIND_MF_AR1_RBF, 3, MF_PARAMS, 700)):
+        X4 = np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (N, 3)), rng.integers(0, F, (N, 1)).astype(float)])
+        y = np.sin(X4[:, 0]) + 0.3 * X4[:, 3] + 0.05 * rng.standard_normal(N)
+        core = gpcore_mod.GPCore(kind, F, 0)
+        core.set_hypers(p, 1e-8)
+        core.set_data(X4, y)
+        core.factor()
+        ref = go.SFGP(X4[:, :3], y, p, gram=False) if F == 1 else go.MFGP(X4, y, p, F=F, gram=False)
+        shapes = [(7, 5, 3), (1, 1, 1), (33, 65, 70), (130, 90, 5)]          # the last one: 11700 pairs -> two passes
+        for (nx, ny, nz) in shapes:
+            ax, ay, az = np.sort(rng.uniform(0, 10, nx)), np.sort(rng.uniform(0, 20, ny)), np.linspace(0.5, 9.5, nz)
+            for f in range(F):
+                got = core.predict_grid_mean(ax, ay, az, fid=f)
+                Xs = mesh(ax, ay, az, f)
+                want, _ = core.predict(Xs, L_.MEAN_ONLY)
+                assert got.shape == (nx, ny, nz)
+                assert np.max(np.abs(got.ravel() - want)) <= 1e-11 * max(1.0, np.max(np.abs(want))), (kind, nx, ny, nz, f)
+                if nx * ny * nz <= 200:
+                    mu, _ = ref.predict(Xs[:, :3] if F == 1 else Xs)
+                    assert np.max(np.abs(got.ravel() - mu[:, 0])) <= 1e-9 * max(1.0, np.max(np.abs(mu)))
+        core.close()
+    core = gpcore_mod.GPCore(L_.KIND_SF_MAT32, 1, 0)
+    core.set_hypers(SF_PARAMS, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    with pytest.raises(Exception):
+        core.predict_grid_mean([0.0, 1.0], [0.0], [0.0])
+    core.close()
+    # the mirrored models expose it next to predict(): emukit wrapper (query fidelity 2) and NIGP (return_var=False)
+    from gpcore.GPy.kern import RBF
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    from gpcore.nigp import NIGP
+    k = LinearMultiFidelityKernel([RBF(3, ARD=True) for _ in range(3)])
+    mf = GPyMultiOutputWrapper(GPyLinearMultiFidelityModel(X4, y[:, None], k, n_fidelities=3), 3, 1)
+    mf.gpy_model.param_array[:] = MF_PARAMS
+    ax, ay, az = np.linspace(0, 10, 9), np.linspace(0, 20, 11), np.linspace(0, 10, 4)
+    mu, _ = mf.predict(mesh(ax, ay, az, 2))
+    assert np.max(np.abs(mf.predict_grid_mean(ax, ay, az, fid=2).ravel() - mu[:, 0])) < 1e-11 * max(1.0, np.max(np.abs(mu)))
+    g, d = golden("nigp_field.npz"), golden("field_data.npz")
+    m = NIGP(verbose=False)
+    m.lengthscales_, m.sigma_f_, m.sigma_y_, m.sigma_x_ = g["ls"], float(g["sigma_f"]), float(g["sigma_y"]), g["sigma_x"]
+    m.X_train_, m.y_train_, m.noise_diag_train_ = d["Xh"], d["y"], g["noise_diag"]
+    want = m.predict(mesh(ax, ay, az, 0)[:, :3], return_var=False)
+    assert np.max(np.abs(m.predict_grid_mean(ax, ay, az).ravel() - want)) < 1e-11 * max(1.0, np.max(np.abs(want)))

@@ -673,7 +673,7 @@ def main():
                          "fp64 = DMMA")
     ap.add_argument("--n-train", type=int, default=0)
     ap.add_argument("--m-test", type=int, default=0)
-    ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--ig", type=int, default=1)
     ap.add_argument("--ig-candidates", type=int, default=65536)
     args = ap.parse_args()

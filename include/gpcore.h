@@ -207,7 +207,7 @@ int gpc_spd_stats(gpc_handle h, const double* cov, long M, const double* e, doub
 /* ---- measurement hooks ---------------------------------------------------------------------- */
 void* gpc_stream(gpc_handle h);                 /* cudaStream_t all kernels are launched on     */
 long gpc_launch_count(gpc_handle h);            /* kernels launched by this handle so far        */
-int gpc_set_chunk(gpc_handle h, long m_chunk);  /* test points per launch batch (default 16384)  */
+int gpc_set_chunk(gpc_handle h, long m_chunk);  /* test points per launch batch (default 65536)  */
 int gpc_set_mode(gpc_handle h, int mode);       /* GPC_MODE_FP64 | GPC_MODE_INT8                   */
 int gpc_get_mode(gpc_handle h);
 /* Device time of the dominant kernel (the L^-1 K* DMMA contraction) accumulated with CUDA events

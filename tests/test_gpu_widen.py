@@ -512,3 +512,41 @@ def test_tensor_grid_mean_as_gemm(gpcore_mod, go):
     m.X_train_, m.y_train_, m.noise_diag_train_ = d["Xh"], d["y"], g["noise_diag"]
     want = m.predict(mesh(ax, ay, az, 0)[:, :3], return_var=False)
     assert np.max(np.abs(m.predict_grid_mean(ax, ay, az).ravel() - want)) < 1e-11 * max(1.0, np.max(np.abs(want)))
+
+
+def test_reference_information_gain_script(gpcore_mod, go):
+    """examples/information_gain_test.py = the reference's informationGainTest.py with the GPy import swapped; the
+    same flow on the oracle's GPRegression restatement gives the numbers to compare with (1-D inputs, non-ARD RBF,
+    assignment to Gaussian_noise.variance, set_XY to a single far-away prior point, full_cov predictions)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("information_gain_test", os.path.join(root, "examples", "information_gain_test.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for seed, n in ((0, 3), (1, 6), (2, 12)):
+        I, I2, I3 = mod.run(seed, n, verbose=False)
+        np.random.seed(seed)
+        Xpred = np.array([np.arange(-3, 3, .1)]).T
+        X = np.random.uniform(-3., 3., (n, 1))
+        Y = np.sin(X) + np.random.randn(n, 1) * 0.05
+        p = np.array([0.7407926234918235, 1.5704374366230516, 0.0010413149736387451])
+        pad = lambda A: np.hstack([A, np.zeros((len(A), 2))])
+        p5 = np.array([p[0], p[1], p[1], p[1], p[2]])
+        ld = lambda K: np.linalg.slogdet(K)[1]
+        g = go.SFGP(pad(np.array([[-100.0]])), np.array([[0.0]]), p5, gram=False)
+        lp, lp2 = ld(g.predict(pad(Xpred), full_cov=True)[1]), ld(g.predict(pad(X), full_cov=True)[1])
+        g.set_XY(pad(X), Y)
+        wI = 0.5 * (lp - ld(g.predict(pad(Xpred), full_cov=True)[1]))
+        wI3 = 0.5 * (lp2 - ld(g.predict(pad(X), full_cov=True)[1]))
+        g.set_XY(pad(X[:1]), np.array([[0.0]]))
+        wI2 = 0.5 * np.log(1 + g.predict(pad(X[:1]))[1][0, 0] / p[2])
+        Xa = X[:1]
+        for i in range(2, n):
+            wI2 += 0.5 * np.log(1 + g.predict(pad(X[i:i + 1]))[1][0, 0] / p[2])
+            Xa = np.concatenate((Xa, X[i:i + 1]))
+            g.set_XY(pad(Xa), np.zeros((len(Xa), 1)))
+        # the 60-point grid covariance is numerically singular (det ~ 1e-200): log-dets agree to ~1e-6 between LAPACKs
+        assert abs(I - wI) < 1e-5 * max(1.0, abs(wI)), (seed, I, wI)
+        assert abs(I2 - wI2) < 1e-8 * max(1.0, abs(wI2)), (seed, I2, wI2)
+        assert abs(I3 - wI3) < 1e-7 * max(1.0, abs(wI3)), (seed, I3, wI3)

@@ -441,7 +441,10 @@ class GPRegression(_DeviceGP):
     """``GPy.models.GPRegression(X, Y, kernel, noise_var=1.)`` -- zero mean, Gaussian likelihood.
     ``param_array = [variance, lengthscale(D | 1), noise_var]``."""
 
-    def __init__(self, X, Y, kernel=None, noise_var=1.0, device=0):
+    def __init__(self, X, Y, kernel=None, Y_metadata=None, normalizer=None, noise_var=1.0, mean_function=None, device=0):
+        # GPy's signature; the reference only ever passes mean_function=None (HowManyPoints.py:91-92)
+        if mean_function is not None or normalizer not in (None, False):
+            raise NotImplementedError("gpcore mirrors the zero-mean, un-normalised GPRegression the reference uses")
         X = np.asarray(X, dtype=float)
         if kernel is None:
             kernel = RBF(X.shape[1])

@@ -49,6 +49,10 @@ def test_no_cpu_fallback(built_lib):
     m = GPRegression(np.zeros((4, 3)), np.zeros((4, 1)), RBF(3, ARD=True))   # host state only
     with pytest.raises(gpcore.GpcoreError):
         m.predict(np.zeros((2, 3)))
+    # GPy's keyword signature as HowManyPoints.py:91-92 calls it; anything but the zero mean is refused loudly
+    GPRegression(np.zeros((4, 3)), np.zeros((4, 1)), RBF(input_dim=3, variance=1, lengthscale=1, ARD=True), mean_function=None)
+    with pytest.raises(NotImplementedError):
+        GPRegression(np.zeros((4, 3)), np.zeros((4, 1)), RBF(3), mean_function=object())
 
 
 def test_param_array_layout_and_views():

@@ -25,9 +25,11 @@
 //   warp 0   TMA producer (one lane): 3-stage ring of (A k-block, B k-block) = 72 KB per stage
 //   warp 1   MMA issuer (one lane): 16 tcgen05.mma.kind::i8 (M = 128, N = 64..256, K = 32) per stage into
 //            S accumulators of 64 TMEM columns; tcgen05.commit frees the stage / publishes the tile
-//   warps 2-5 epilogue: tcgen05.ld the S int32 levels, recombine in int64, scale to FP64 and either
-//            reduce sum_i V(n, i)^2 per test row (one thread owns a row: no shuffles) or store V.
-// The schedule is the one of k_vt: item (mt, p) = train tiles nb2-1-p then p of test tile mt.
+//   warps 2-5 epilogue: tcgen05.ld the S int32 levels (software-pipelined), recombine in int64, scale to FP64 and
+//            reduce sum_i V(n, i)^2 per test row (one thread owns a row: no shuffles), store V, or emit V's own
+//            digit image for the next INT8 product (information gain).
+// Schedules: triangular -- item (mt, p) = train tiles nb2-1-p then p of test tile mt (V = K* X^T, X lower
+// triangular) -- or full-K (Gram and cross products of V); see the comment above k_vt_i8.
 #pragma once
 #include "gpc_common.cuh"
 
@@ -80,14 +82,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -127,24 +121,6 @@ __device__ __forceinline__ uint4 pack_slice(const unsigned long long (&u)[16], i
     w[q] = (x[0] | (x[1] << 8) | (x[2] << 16) | (x[3] << 24)) ^ 0x80808080u;  // digit = byte - 128
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// 8-value variant: half of a 16-byte chunk.
-__device__ __forceinline__ uint2 pack_slice8(const unsigned long long (&u)[8], int p) {
-  const int b = S - 1 - p;
-  uint32_t w[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint32_t x[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const unsigned long long v = u[4 * q + e];
-      const uint32_t word = b < 4 ? (uint32_t)v : (uint32_t)(v >> 32);
-      x[e] = (word >> (8 * (b & 3))) & 255u;
-    }
-    w[q] = (x[0] | (x[1] << 8) | (x[2] << 16) | (x[3] << 24)) ^ 0x80808080u;
-  }
-  return make_uint2(w[0], w[1]);
 }
 
 }  // namespace gpoz
@@ -188,16 +164,6 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
 #pragma unroll
     for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(base + (long)p * B_SLICE) = pack_slice(uu, p);
   }
-}
-
-// Byte B of four 48-bit values -> 4 digit bytes of one slice.
-template <int B>
-__device__ __forceinline__ uint32_t pack_bytes4(const unsigned long long (&u)[4]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) w[e] = B < 4 ? (uint32_t)u[e] : (uint32_t)(u[e] >> 32);
-  constexpr uint32_t sel = (uint32_t)(B & 3) | ((uint32_t)(4 + (B & 3)) << 4);
-  return __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410) ^ 0x80808080u;
 }
 
 // Byte b (0 = least significant) of eight 48-bit values -> the 8 digit bytes of one slice (PRMT).

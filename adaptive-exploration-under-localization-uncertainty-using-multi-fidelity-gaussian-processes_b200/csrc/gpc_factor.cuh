@@ -78,63 +78,93 @@ __global__ void __launch_bounds__(GPC_PD_NT, 1) k_potrf_diag(double* __restrict_
   }
   __syncthreads();
 
+  // Software pipeline over the eight 16-column steps: while warps 1..15 apply the rank-16 update of step kb,
+  // warp 0 updates just the NEXT 16 x 16 diagonal sub-block and factors / inverts it (the serial part of step
+  // kb + 1), so that it is off the critical path of every step but the first.
+  auto factor16 = [&](int c0) {
+    // (1) 16 x 16 diagonal sub-block: lane l owns row l in registers; the pivot's reciprocal
+    //     square root and the column of multipliers travel through shared memory (broadcast
+    //     reads), two __syncwarp per column -- no shuffle chains on the critical path.
+    const int l = lane & 15;  // lanes 16..31 shadow lanes 0..15
+    double* colb = S + 128 * GPC_PD_LD;  // 16 multipliers
+    double* invs = colb + 16;          // 16 reciprocal pivots
+    double a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (j <= l) ? S[(c0 + l) * GPC_PD_LD + c0 + j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (lane == k) {
+        double d = a[k];
+        if (!(d > 0.0)) { bad = 1; d = 1.0; }
+        double inv = rsqrt(d);
+        inv = inv * fma(-0.5 * d * inv, inv, 1.5);  // one more Newton step: full double accuracy
+        invs[k] = inv;
+      }
+      __syncwarp();
+      const double inv = invs[k];
+      if (l == k) a[k] *= inv;  // d / sqrt(d) = sqrt(d)
+      else if (l > k) {
+        a[k] *= inv;
+        if (lane < 16) colb[l] = a[k];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = k + 1; j < 16; ++j)
+        if (l >= j) a[j] = fma(-a[k], colb[j], a[j]);
+    }
+    if (lane < 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j <= l) S[(c0 + l) * GPC_PD_LD + c0 + j] = a[j];
+    }
+    __syncwarp();
+    // T = L_kk^-1, column l per lane, right-looking; L is read back from shared memory (broadcast)
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x[k] *= invs[k];
+#pragma unroll
+      for (int i = k + 1; i < 16; ++i) x[i] = fma(-S[(c0 + i) * GPC_PD_LD + c0 + k], x[k], x[i]);
+    }
+    if (lane < 16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i >= l) XT(c0 + i, c0 + l) = x[i];
+    }
+  };
+  auto chol_tile = [&](int r0, int c0, int ti, int tj) {
+    double c[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
+    const double* Pi = S + (r0 + 4 * ti) * GPC_PD_LD + c0;
+    const double* Pj = S + (r0 + 4 * tj) * GPC_PD_LD + c0;
+#pragma unroll 4
+    for (int m = 0; m < 16; ++m) {
+      double ai[4], aj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { ai[u] = Pi[u * GPC_PD_LD + m]; aj[u] = Pj[u * GPC_PD_LD + m]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], aj[v], c[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = r0 + 4 * ti + u, j = r0 + 4 * tj + v;
+        if (j <= i) S[i * GPC_PD_LD + j] -= c[u][v];
+      }
+  };
+  if (warp == 0) factor16(0);
+  __syncthreads();
 #pragma unroll 1
   for (int kb = 0; kb < 8; ++kb) {
     const int c0 = kb * 16;
-    if (warp == 0) {
-      // (1) 16 x 16 diagonal sub-block: lane l owns row l in registers; the pivot's reciprocal
-      //     square root and the column of multipliers travel through shared memory (broadcast
-      //     reads), two __syncwarp per column -- no shuffle chains on the critical path.
-      const int l = lane & 15;  // lanes 16..31 shadow lanes 0..15
-      double* colb = S + 128 * GPC_PD_LD;  // 16 multipliers
-      double* invs = colb + 16;            // 16 reciprocal pivots
-      double a[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = (j <= l) ? S[(c0 + l) * GPC_PD_LD + c0 + j] : 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        if (lane == k) {
-          double d = a[k];
-          if (!(d > 0.0)) { bad = 1; d = 1.0; }
-          double inv = rsqrt(d);
-          inv = inv * fma(-0.5 * d * inv, inv, 1.5);  // one more Newton step: full double accuracy
-          invs[k] = inv;
-        }
-        __syncwarp();
-        const double inv = invs[k];
-        if (l == k) a[k] *= inv;  // d / sqrt(d) = sqrt(d)
-        else if (l > k) {
-          a[k] *= inv;
-          if (lane < 16) colb[l] = a[k];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = k + 1; j < 16; ++j)
-          if (l >= j) a[j] = fma(-a[k], colb[j], a[j]);
-      }
-      if (lane < 16) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j <= l) S[(c0 + l) * GPC_PD_LD + c0 + j] = a[j];
-      }
-      __syncwarp();
-      // T = L_kk^-1, column l per lane, right-looking; L is read back from shared memory (broadcast)
-      double x[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        x[k] *= invs[k];
-#pragma unroll
-        for (int i = k + 1; i < 16; ++i) x[i] = fma(-S[(c0 + i) * GPC_PD_LD + c0 + k], x[k], x[i]);
-      }
-      if (lane < 16) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i >= l) XT(c0 + i, c0 + l) = x[i];
-      }
-    }
-    __syncthreads();
     const int r0 = c0 + 16, nrow = 128 - r0;
     if (tid < nrow) {
       // (2a) panel: L[r][c0 + c] = sum_{m <= c} A[r][c0 + m] T[c][m]
@@ -168,58 +198,53 @@ __global__ void __launch_bounds__(GPC_PD_NT, 1) k_potrf_diag(double* __restrict_
       for (int i = 0; i < 16; ++i) XT(c0 + i, j) = out[i];
     }
     __syncthreads();
-    // (3) rank-16 updates in 4 x 4 micro-tiles: first the trailing Cholesky tiles (lower triangle of
-    //     nt x nt), then the inverse's right-hand side Y[r][c] -= L[r][c0:c0+16] X[c0:c0+16][c], c < r0
+    // (3) rank-16 updates in 4 x 4 micro-tiles: the trailing Cholesky tiles (lower triangle of nt x nt) and the
+    //     inverse's right-hand side Y[r][c] -= L[r][c0:c0+16] X[c0:c0+16][c], c < r0.  Warp 0 takes the ten tiles of
+    //     the next diagonal sub-block and goes on to factor it; the other warps share everything else.
     const int nt = nrow >> 2, nchol = nt * nt, ncx = r0 >> 2, ntot = nchol + nt * ncx;
-    for (int idx = tid; idx < ntot; idx += GPC_PD_NT) {
-      double c[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
-      if (idx < nchol) {
-        const int ti = idx / nt, tj = idx - ti * nt;
-        if (tj > ti) continue;
-        const double* Pi = S + (r0 + 4 * ti) * GPC_PD_LD + c0;
-        const double* Pj = S + (r0 + 4 * tj) * GPC_PD_LD + c0;
-#pragma unroll 4
-        for (int m = 0; m < 16; ++m) {
-          double ai[4], aj[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { ai[u] = Pi[u * GPC_PD_LD + m]; aj[u] = Pj[u * GPC_PD_LD + m]; }
+    if (warp == 0) {
+      if (nt > 0) {
+        if (lane < 10) {
+          const int ti = lane < 1 ? 0 : (lane < 3 ? 1 : (lane < 6 ? 2 : 3));
+          const int tj = lane - (ti * (ti + 1)) / 2;
+          chol_tile(r0, c0, ti, tj);
+        }
+        __syncwarp();
+        factor16(r0);
+      }
+    } else {
+      for (int idx = tid - 32; idx < ntot; idx += GPC_PD_NT - 32) {
+        if (idx < nchol) {
+          const int ti = idx / nt, tj = idx - ti * nt;
+          if (tj > ti || ti < 4) continue;          // upper triangle / warp 0's tiles
+          chol_tile(r0, c0, ti, tj);
+        } else {
+          double c[4][4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], aj[v], c[u][v]);
-        }
+            for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
+          const int e = idx - nchol;
+          const int ti = e / ncx, tc = e - ti * ncx;
+          const int rr = r0 + 4 * ti, cc = 4 * tc;
+          const double* Pi = S + rr * GPC_PD_LD + c0;
+#pragma unroll 4
+          for (int m = 0; m < 16; ++m) {
+            double ai[4], xv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u) ai[u] = Pi[u * GPC_PD_LD + m];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int i = r0 + 4 * ti + u, j = r0 + 4 * tj + v;
-            if (j <= i) S[i * GPC_PD_LD + j] -= c[u][v];
+            for (int v = 0; v < 4; ++v) xv[v] = (c0 + m >= cc + v) ? XT(c0 + m, cc + v) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], xv[v], c[u][v]);
           }
-      } else {
-        const int e = idx - nchol;
-        const int ti = e / ncx, tc = e - ti * ncx;
-        const int rr = r0 + 4 * ti, cc = 4 * tc;
-        const double* Pi = S + rr * GPC_PD_LD + c0;
-#pragma unroll 4
-        for (int m = 0; m < 16; ++m) {
-          double ai[4], xv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) ai[u] = Pi[u * GPC_PD_LD + m];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) xv[v] = (c0 + m >= cc + v) ? XT(c0 + m, cc + v) : 0.0;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], xv[v], c[u][v]);
+            for (int v = 0; v < 4; ++v) XT(rr + u, cc + v) -= c[u][v];
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) XT(rr + u, cc + v) -= c[u][v];
       }
     }
     __syncthreads();

@@ -50,6 +50,7 @@ struct gpc_handle_s {
   cudaStream_t stream = nullptr, side = nullptr;   // side: look-ahead stream of the factorisation
   cudaStream_t inv = nullptr;                      // early part of the triangular inverse (runs under the Cholesky tail)
   cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_half = nullptr, ev_inv = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};   // host-buffer predict
   GpcHyp hyp;
   bool have_hyp = false, have_data = false, factored = false;
   long N = 0, n_pad = 0;
@@ -590,6 +591,11 @@ int gpc_create(int kind, int F, int device, gpc_handle* out) {
   e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_mid);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->inv, cudaStreamNonBlocking, prio_lo);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cmp[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_half, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming);
 
@@ -631,6 +637,11 @@ int gpc_destroy(gpc_handle h) {
   }
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_cmp[i]) cudaEventDestroy(h->ev_cmp[i]);
+    if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+  }
   if (h->ev_half) cudaEventDestroy(h->ev_half);
   if (h->ev_inv) cudaEventDestroy(h->ev_inv);
   if (h->side) cudaStreamDestroy(h->side);
@@ -960,7 +971,7 @@ int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, dou
 // GPC_STAGE_ROWS rows (one H2D copy, m_chunk-row launches back to back with no host sync in
 // between, one D2H copy per output), so copies and kernels queue up on the stream instead of
 // ping-ponging with the host once per launch.
-#define GPC_STAGE_ROWS (1L << 22)
+#define GPC_STAGE_ROWS (1L << 18)
 static int predict_host(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows, double* mean,
                         double* var, unsigned flags) {
   int rc = require_factor(h);
@@ -971,28 +982,53 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
     return fail(h, GPC_ERR_ARG, "input-noise correction is defined for the single-fidelity squared-exponential kernel");
   if (M == 0) return GPC_OK;
   CK(cudaSetDevice(h->device));
-  const long mc = h->m_chunk;
-  const long stage = M < GPC_STAGE_ROWS ? round_up(M, 128) : GPC_STAGE_ROWS;
-  CK(h->Xs4.ensure((size_t)stage * 32));
-  CK(h->mean.ensure((size_t)stage * 8));
-  CK(h->var.ensure((size_t)stage * 8));
+  // Two device stages alternate.  The copy stream (in order) carries  in(0), in(1), out(0), in(2), out(1), ... : the
+  // host -> device copy of stage s + 1 and the device -> host copy of stage s - 1 run while the compute stream works
+  // on stage s; the host synchronises once, at the end.
+  const long stage = M <= GPC_STAGE_ROWS ? round_up(M, 128) : GPC_STAGE_ROWS;
+  const int nbuf = M > stage ? 2 : 1;
+  CK(h->Xs4.ensure((size_t)nbuf * stage * 32));
+  CK(h->mean.ensure((size_t)nbuf * stage * 8));
+  CK(h->var.ensure((size_t)nbuf * stage * 8));
+  cudaStream_t sc = h->stream, sio = h->side;
+  const bool per_row_sx = sx && sx_rows != 1;
   if (sx) {
-    CK(h->ediag.ensure((size_t)(sx_rows == 1 ? 1 : stage) * 24));
-    if (sx_rows == 1) CK(cudaMemcpyAsync(h->ediag.p, sx, 24, cudaMemcpyHostToDevice, h->stream));
+    CK(h->ediag.ensure((size_t)(per_row_sx ? nbuf * stage : 1) * 24));
+    if (!per_row_sx) CK(cudaMemcpyAsync(h->ediag.p, sx, 24, cudaMemcpyHostToDevice, sc));
   }
   const bool want_var = var && !(flags & GPC_MEAN_ONLY);
-  for (long s0 = 0; s0 < M; s0 += stage) {
-    const long ms = (M - s0) < stage ? (M - s0) : stage;
-    CK(cudaMemcpyAsync(h->Xs4.p, Xs4 + s0 * 4, (size_t)ms * 32, cudaMemcpyHostToDevice, h->stream));
-    if (sx && sx_rows != 1)
-      CK(cudaMemcpyAsync(h->ediag.p, sx + s0 * 3, (size_t)ms * 24, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = predict_rows(h, h->Xs4.d(), ms, mean ? h->mean.d() : nullptr, want_var ? h->var.d() : nullptr, flags,
-                           sx ? h->ediag.d() : nullptr, sx_rows)))
-      return rc;
-    if (mean) CK(cudaMemcpyAsync(mean + s0, h->mean.p, (size_t)ms * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (want_var) CK(cudaMemcpyAsync(var + s0, h->var.p, (size_t)ms * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventRecord(h->ev_cmp[0], sc));            // the copy stream starts behind everything queued so far
+  CK(cudaStreamWaitEvent(sio, h->ev_cmp[0], 0));
+  auto copy_in = [&](long si) -> int {
+    const long s0 = si * stage, ms = (M - s0) < stage ? (M - s0) : stage;
+    const int b = (int)(si % nbuf);
+    CK(cudaMemcpyAsync(h->Xs4.d() + (size_t)b * stage * 4, Xs4 + s0 * 4, (size_t)ms * 32, cudaMemcpyHostToDevice, sio));
+    if (per_row_sx)
+      CK(cudaMemcpyAsync(h->ediag.d() + (size_t)b * stage * 3, sx + s0 * 3, (size_t)ms * 24, cudaMemcpyHostToDevice, sio));
+    CK(cudaEventRecord(h->ev_h2d[b], sio));
+    return GPC_OK;
+  };
+  const long nstage = (M + stage - 1) / stage;
+  if ((rc = copy_in(0))) return rc;
+  for (long si = 0; si < nstage; ++si) {
+    const long s0 = si * stage, ms = (M - s0) < stage ? (M - s0) : stage;
+    const int b = (int)(si % nbuf);
+    double* dX = h->Xs4.d() + (size_t)b * stage * 4;
+    double* dm = h->mean.d() + (size_t)b * stage;
+    double* dv = h->var.d() + (size_t)b * stage;
+    const double* de = sx ? (per_row_sx ? h->ediag.d() + (size_t)b * stage * 3 : h->ediag.d()) : nullptr;
+    CK(cudaStreamWaitEvent(sc, h->ev_h2d[b], 0));                       // inputs of this stage have landed
+    if (si >= 2) CK(cudaStreamWaitEvent(sc, h->ev_d2h[b], 0));          // results of stage s - 2 have left these buffers
+    if ((rc = predict_rows(h, dX, ms, mean ? dm : nullptr, want_var ? dv : nullptr, flags, de, sx_rows))) return rc;
+    CK(cudaEventRecord(h->ev_cmp[b], sc));
+    if (si + 1 < nstage && (rc = copy_in(si + 1))) return rc;           // queued BEFORE out(s): it must not wait for compute(s)
+    CK(cudaStreamWaitEvent(sio, h->ev_cmp[b], 0));
+    if (mean) CK(cudaMemcpyAsync(mean + s0, dm, (size_t)ms * 8, cudaMemcpyDeviceToHost, sio));
+    if (want_var) CK(cudaMemcpyAsync(var + s0, dv, (size_t)ms * 8, cudaMemcpyDeviceToHost, sio));
+    CK(cudaEventRecord(h->ev_d2h[b], sio));
   }
+  CK(cudaStreamSynchronize(sio));
+  CK(cudaStreamSynchronize(sc));
   return GPC_OK;
 }
 

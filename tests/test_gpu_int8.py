@@ -147,3 +147,31 @@ def test_int8_information_gain_matches_fp64(gpcore_mod, go, scale, noise):
     want = np.array([go.ig_logdet_refit(ref, g4, c) if len(c) else 0.0 for c in cands[:4]])
     assert normwise(out[L_.MODE_INT8][1][:4], want, 1.0) < 1e-7
     core.close()
+
+
+def test_int8_size_limit_and_fallback(gpcore_mod):
+    """N = 16384 is the largest training set the INT8 path takes (int32 accumulators: 6 digit pairs x K x 128^2 < 2^31);
+    one row more and the same call runs on the FP64 DMMA path.  Both sides of the limit against each other on the same
+    problem (size-independent property: the two contractions compute the same V), plus chunk-boundary row counts."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(16384)
+    X4, y = synth(rng, 16385, 1)
+    Xs4 = np.hstack([rng.uniform(0, 10, (1025, 3)), np.zeros((1025, 1))])
+    Xs4[:200, :3] = X4[:200, :3] + 1e-3
+    flags = L_.INCLUDE_NOISE | L_.CLIP_DIAG
+    res = {}
+    for N in (16384, 16385):
+        core = gpcore_mod.GPCore(L_.KIND_SF_RBF, 1, 0)
+        core.set_hypers(SF_PARAMS, 1e-8)
+        core.set_data(X4[:N], y[:N])
+        core.factor()
+        assert core.mode() == L_.MODE_INT8
+        m1, v1 = core.predict(Xs4, flags)
+        core.set_mode(L_.MODE_FP64)
+        m0, v0 = core.predict(Xs4, flags)
+        assert normwise(m1, m0) < 1e-12 and normwise(v1, v0, SF_PARAMS[0]) < 1e-9, N
+        assert np.all(v1 >= SF_PARAMS[-1] * (1 - 1e-9)) and np.all(v1 <= (SF_PARAMS[0] + SF_PARAMS[-1]) * (1 + 1e-9))
+        res[N] = (m1, v1)
+        core.close()
+    # one more training row barely moves the posterior at points far from it: the two problems agree loosely
+    assert normwise(res[16384][0], res[16385][0]) < 1e-2

@@ -175,3 +175,29 @@ def test_int8_size_limit_and_fallback(gpcore_mod):
         core.close()
     # one more training row barely moves the posterior at points far from it: the two problems agree loosely
     assert normwise(res[16384][0], res[16385][0]) < 1e-2
+
+
+def test_host_predict_stages(gpcore_mod, go):
+    """gpc_predict on host buffers longer than one device stage (2^18 rows): two alternating stages with the copies on
+    a second stream.  A ragged 600001-row call must equal the same rows predicted in small independent calls."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(8)
+    X4, y = synth(rng, 300, 1)
+    core = gpcore_mod.GPCore(L_.KIND_SF_RBF, 1, 0)
+    core.set_hypers(SF_PARAMS, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    M = 600001
+    Xs4 = np.hstack([rng.uniform(0, 10, (M, 3)), np.zeros((M, 1))])
+    flags = L_.INCLUDE_NOISE | L_.CLIP_DIAG
+    m, v = core.predict(Xs4, flags)
+    probes = [0, 1, 262143, 262144, 262145, 524287, 524288, 599999, 600000]
+    for lo in (0, 262000, 524000, 599000):
+        hi = min(M, lo + 1001)
+        m0, v0 = core.predict(np.ascontiguousarray(Xs4[lo:hi]), flags)
+        assert np.array_equal(m[lo:hi], m0) and np.array_equal(v[lo:hi], v0), lo
+    assert np.all(np.isfinite(m[probes])) and np.all(v[probes] > 0)
+    ref = go.SFGP(X4[:, :3], y, SF_PARAMS, gram=False)
+    mu, var = ref.predict(Xs4[probes, :3])
+    assert normwise(m[probes], mu[:, 0]) < TOL and normwise(v[probes], var[:, 0], SF_PARAMS[0]) < TOL
+    core.close()

@@ -267,6 +267,19 @@ int solve_alpha(gpc_handle h) {
   return GPC_OK;
 }
 
+// Fidelity labels of caller rows (x, y, z, fid): integers in [0, F) for a multi-fidelity model (emukit raises on
+// anything else); single-fidelity models ignore the column.
+int check_fidelity_rows(gpc_handle h, const double* X4, long n, const char* what) {
+  if (h->F == 1 || !X4) return GPC_OK;
+  const double F = (double)h->F;
+  for (long i = 0; i < n; ++i) {
+    const double f = X4[i * 4 + 3];
+    if (!(f >= 0.0) || f >= F || f != std::floor(f))
+      return fail(h, GPC_ERR_ARG, std::string(what) + ": fidelity index must be an integer in [0, F)");
+  }
+  return GPC_OK;
+}
+
 int require_factor(gpc_handle h) {
   if (!h) return GPC_ERR_ARG;
   if (!h->factored) return fail(h, GPC_ERR_STATE, "model not factored: call gpc_factor first");
@@ -938,6 +951,7 @@ int gpc_kernel_matrix(gpc_handle h, const double* Xa4, long na, const double* Xb
   if (!h->have_hyp) return fail(h, GPC_ERR_STATE, "set hypers first");
   if (!Xb4) { Xb4 = Xa4; nb_ = na; }
   if (na < 1 || nb_ < 1) return fail(h, GPC_ERR_SHAPE, "empty input");
+  if (check_fidelity_rows(h, Xa4, na, "kernel rows") || check_fidelity_rows(h, Xb4, nb_, "kernel rows")) return GPC_ERR_ARG;
   CK(cudaSetDevice(h->device));
   DevBuf a, b, k;
   cudaError_t e;
@@ -981,6 +995,7 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
   if (sx && (h->F != 1 || h->hyp.base != 0))
     return fail(h, GPC_ERR_ARG, "input-noise correction is defined for the single-fidelity squared-exponential kernel");
   if (M == 0) return GPC_OK;
+  if ((rc = check_fidelity_rows(h, Xs4, M, "test rows"))) return rc;
   CK(cudaSetDevice(h->device));
   // Two device stages alternate.  The copy stream (in order) carries  in(0), in(1), out(0), in(2), out(1), ... : the
   // host -> device copy of stage s + 1 and the device -> host copy of stage s - 1 run while the compute stream works
@@ -1121,6 +1136,7 @@ int gpc_predict_cov(gpc_handle h, const double* Xs4, long M, double* mean, doubl
   if (rc) return rc;
   if (M < 1 || !Xs4 || !cov) return fail(h, GPC_ERR_SHAPE, "bad test set");
   if (M > 32768) return fail(h, GPC_ERR_SHAPE, "full covariance limited to M <= 32768");
+  if ((rc = check_fidelity_rows(h, Xs4, M, "test rows"))) return rc;
   CK(cudaSetDevice(h->device));
   const long m_pad = round_up(M, 128);
   if ((rc = ensure_pred_ws(h, m_pad, true, false))) return rc;

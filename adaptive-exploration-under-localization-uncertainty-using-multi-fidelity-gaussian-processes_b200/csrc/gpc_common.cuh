@@ -27,21 +27,21 @@ __device__ __forceinline__ double gpc_base_k(const GpcHyp& h, int m, double dx, 
   return h.var[m] * (1.0 + r) * exp(-r);
 }
 
+__device__ __forceinline__ int gpc_fid(const GpcHyp& h, double f) {
+  int i = (int)f;
+  return (h.F == 1 || i < 0) ? 0 : (i >= h.F ? h.F - 1 : i);
+}
+
 // k((xa, fa), (xb, fb)): stationary for F == 1, Kennedy-O'Hagan AR1 sum otherwise.
 __device__ __forceinline__ double gpc_kval(const GpcHyp& h, double ax, double ay, double az, double af,
                                            double bx, double by, double bz, double bf) {
   const double dx = ax - bx, dy = ay - by, dz = az - bz;
   if (h.F == 1) return gpc_base_k(h, 0, dx, dy, dz);
-  const int fi = (int)af, fj = (int)bf;
+  const int fi = gpc_fid(h, af), fj = gpc_fid(h, bf);   // the C ABI rejects out-of-range labels; never index past coef
   const int mm = fi < fj ? fi : fj;
   double s = 0.0;
   for (int m = 0; m <= mm; ++m) s = fma(h.coef[fi][m] * h.coef[fj][m], gpc_base_k(h, m, dx, dy, dz), s);
   return s;
-}
-
-__device__ __forceinline__ int gpc_fid(const GpcHyp& h, double f) {
-  int i = (int)f;
-  return (h.F == 1 || i < 0) ? 0 : (i >= h.F ? h.F - 1 : i);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -136,12 +136,9 @@ class _Stationary(_Parameterized):
 
     def K(self, X, X2=None):
         """``kern.K`` evaluated on the device (no noise)."""
-        core = GPCore(L.KIND_SF_MAT32 if self._base else L.KIND_SF_RBF, 1, 0)
-        try:
-            core.set_hypers(self._sf_hypers(), 0.0)
-            return core.kernel_matrix(to_x4(X), None if X2 is None else to_x4(X2))
-        finally:
-            core.close()
+        core = _kernel_core(L.KIND_SF_MAT32 if self._base else L.KIND_SF_RBF, 1, 0)
+        core.set_hypers(self._sf_hypers(), 0.0)
+        return core.kernel_matrix(to_x4(X), None if X2 is None else to_x4(X2))
 
     def Kdiag(self, X):
         return np.full(np.asarray(X).shape[0], float(self._p_variance[0]))
@@ -238,19 +235,37 @@ class LinearMultiFidelityKernel(_Parameterized):
 
     def K(self, X, X2=None):
         """``gpy_model.kern.K(X4)`` (``GraceRIGV3.py:515``): rows carry the fidelity index last."""
-        core = GPCore(L.KIND_MF_AR1_MAT32 if self._base else L.KIND_MF_AR1_RBF, self.n_fidelities, 0)
-        try:
-            core.set_hypers(self._mf_hypers(np.ones(1)), 0.0)
-            return core.kernel_matrix(_x4_mf(X), None if X2 is None else _x4_mf(X2))
-        finally:
-            core.close()
+        F = self.n_fidelities
+        core = _kernel_core(L.KIND_MF_AR1_MAT32 if self._base else L.KIND_MF_AR1_RBF, F, 0)
+        core.set_hypers(self._mf_hypers(np.ones(1)), 0.0)
+        return core.kernel_matrix(_x4_mf(X, F), None if X2 is None else _x4_mf(X2, F))
 
 
-def _x4_mf(X):
+_KERNEL_CORES = {}
+
+
+def _kernel_core(kind, F, device):
+    """One cached handle per (kind, F, device) for ``kern.K`` calls (a handle owns three streams and ~17 events:
+    creating and destroying one per call costs more than the kernel matrix of a planner-sized input)."""
+    key = (int(kind), int(F), int(device))
+    core = _KERNEL_CORES.get(key)
+    if core is None or getattr(core, "h", None) is None:
+        core = _KERNEL_CORES[key] = GPCore(kind, F, device)
+    return core
+
+
+def _x4_mf(X, n_fidelities=None):
     """(n, D + 1) rows with the fidelity index last -> (n, 4) rows; 3-D inputs already have the
-    device row layout (x, y, z, fid) and pass through without a copy."""
+    device row layout (x, y, z, fid) and pass through without a copy.  With ``n_fidelities`` the labels are
+    validated the way emukit does (integers in [0, F)) -- ``ValueError`` otherwise; the C ABI re-checks."""
     X = np.asarray(X, dtype=float)
-    if X.ndim == 2 and X.shape[1] == 4 and X.flags["C_CONTIGUOUS"]:
+    if X.ndim != 2 or X.shape[1] < 2:
+        raise ValueError("multi-fidelity inputs are (n, D + 1) rows with the fidelity index in the last column")
+    if n_fidelities is not None and X.shape[0]:
+        f = X[:, -1]
+        if not (np.all(f >= 0) and np.all(f < n_fidelities) and np.all(f == np.floor(f))):
+            raise ValueError("fidelity index (last input column) must be an integer in [0, %d)" % n_fidelities)
+    if X.shape[1] == 4 and X.flags["C_CONTIGUOUS"]:
         return X
     return to_x4(X[:, :-1], X[:, -1])
 
@@ -265,6 +280,40 @@ def _softplus_inv(v):
 
 def _softplus(x):
     return np.where(x > 30, x, np.log1p(np.exp(np.minimum(x, 30))))
+
+
+def _transforms(lo, hi):
+    """GPy's parameter transforms for a vector of free parameters: Logexp (softplus) where ``hi`` is infinite,
+    Logistic for ``constrain_bounded(lo, hi)``:
+        theta = lo + (hi - lo) / (1 + exp(-x)),  d theta / dx = (theta - lo)(hi - theta) / (hi - lo)
+    -- smooth and strictly inside the bounds, so the optimiser never sees a flat objective with a non-zero gradient.
+    Returns (from_raw, dtheta_dx, to_raw)."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    bounded = np.isfinite(hi)
+    span = hi[bounded] - lo[bounded]
+
+    def from_raw(x):
+        x = np.asarray(x, float)
+        th = np.empty_like(x)
+        th[~bounded] = _softplus(x[~bounded])
+        th[bounded] = lo[bounded] + span / (1.0 + np.exp(-np.clip(x[bounded], -700.0, 700.0)))
+        return th
+
+    def dtheta_dx(th):
+        d = np.empty_like(th)
+        d[~bounded] = -np.expm1(-th[~bounded])                       # d softplus / dx = 1 - exp(-theta)
+        d[bounded] = (th[bounded] - lo[bounded]) * (hi[bounded] - th[bounded]) / span
+        return d
+
+    def to_raw(th):
+        th = np.asarray(th, float)
+        x = np.empty_like(th)
+        x[~bounded] = _softplus_inv(np.maximum(th[~bounded], 1e-12))
+        u = np.clip((th[bounded] - lo[bounded]) / span, 1e-12, 1.0 - 1e-12)   # a start on / outside a bound moves inside
+        x[bounded] = np.log(u) - np.log1p(-u)
+        return x
+
+    return from_raw, dtheta_dx, to_raw
 
 
 class _DeviceGP:
@@ -362,7 +411,8 @@ class _DeviceGP:
 
     def optimize(self, max_iters=1000, messages=False, analytic_gradients=True, **_):
         """``model.optimize()`` (``GPTrainers.py:68,84,94``): L-BFGS-B on the NLML, positive
-        parameters through GPy's default Logexp (softplus) transform, fixed ones left alone.
+        parameters through GPy's default Logexp (softplus) transform, ``constrain_bounded`` ones through
+        its Logistic transform (``...MFGP.py:408-410,664-666``), fixed ones left alone.
         Every evaluation is one device assembly + Cholesky (+ the analytic gradient, about half a
         factorisation more); ``analytic_gradients=False`` falls back to forward differences."""
         mask, bounds = self._free_mask()
@@ -371,12 +421,9 @@ class _DeviceGP:
             return self
         start = self.param_array.copy()
 
-        def from_raw(x):
-            th = _softplus(x)
-            for j, i in enumerate(idx):
-                if bounds[i] is not None:
-                    th[j] = min(max(th[j], bounds[i][0]), bounds[i][1])
-            return th
+        lo = np.array([bounds[i][0] if bounds[i] is not None else 0.0 for i in idx], float)
+        hi = np.array([bounds[i][1] if bounds[i] is not None else np.inf for i in idx], float)
+        from_raw, dtheta_dx, to_raw = _transforms(lo, hi)
 
         def f(x):
             th = from_raw(x)
@@ -387,12 +434,12 @@ class _DeviceGP:
                     raise np.linalg.LinAlgError("non-finite objective")
                 if not analytic_gradients:
                     return v
-                g = self.objective_function_gradients()[idx] * (-np.expm1(-th))   # d softplus / dx = 1 - exp(-theta)
+                g = self.objective_function_gradients()[idx] * dtheta_dx(th)
             except np.linalg.LinAlgError:
                 return (1e25, np.zeros(idx.size)) if analytic_gradients else 1e25
             return v, g
 
-        x0 = _softplus_inv(np.maximum(start[idx], 1e-12))
+        x0 = to_raw(start[idx])
         best_x = x0
         first = f(x0)
         best_f = first[0] if analytic_gradients else first
@@ -528,7 +575,7 @@ class GPyLinearMultiFidelityModel(_DeviceGP):
         return self.kern._mf_hypers(self._noise_vec())
 
     def _X4(self):
-        return _x4_mf(self.X)
+        return _x4_mf(self.X, self.n_fidelities)
 
     def objective_function_gradients(self):
         F = self.n_fidelities
@@ -559,7 +606,7 @@ class GPyLinearMultiFidelityModel(_DeviceGP):
 
     def predict(self, Xnew, full_cov=False, include_likelihood=True, Y_metadata=None, **_):
         core = self._ensure_factor()
-        Xs4 = _x4_mf(Xnew)
+        Xs4 = _x4_mf(Xnew, self.n_fidelities)
         noise = L.INCLUDE_NOISE if include_likelihood else 0
         if full_cov:
             mu, cov = core.predict_cov(Xs4, noise)
@@ -599,7 +646,7 @@ class GPyMultiOutputWrapper:
         """Full posterior covariance, clipped element-wise at 1e-10 like the emukit wrapper."""
         core = self.gpy_model._ensure_factor()
         flags = (L.INCLUDE_NOISE if with_noise else 0) | L.CLIP_COV
-        _, cov = core.predict_cov(_x4_mf(X), flags, want_mean=False)
+        _, cov = core.predict_cov(_x4_mf(X, self.gpy_model.n_fidelities), flags, want_mean=False)
         return cov
 
     def optimize(self):

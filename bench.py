@@ -225,6 +225,38 @@ def run_reference(args):
     emit(line)
 
 
+def oracle_parity(args, X4, y, noise_diag, Xs4_host, dmean, dvar, predict_api, nigp_mode, n=4096):
+    """max_rel_* are NORMWISE (max|gpu - ref| / max(|ref|, prior variance), the 1e-9 criterion of the test-suite);
+    max_elem_rel_var is the element-wise relative error of the variances (bounded below by the noise)."""
+    from oracle import gp_oracle as go
+    M = Xs4_host.shape[0]
+    idx = np.unique(np.linspace(0, M - 1, n).astype(np.int64))
+    Xq = np.ascontiguousarray(Xs4_host[idx])
+    t0 = time.perf_counter()
+    if nigp_mode:
+        mu, var = go.nigp_predict(X4[:, :3], y, NIGP_HYP["ls"], NIGP_HYP["sigma_f"], NIGP_HYP["sigma_y"], noise_diag,
+                                  Xq[:, :3], gram=False)
+        scale, what = float(NIGP_HYP["sigma_f"]), "oracle.gp_oracle.nigp_predict (NIGP.py:269-333 restated, direct distances)"
+        mu_h, var_h = predict_api(np.ascontiguousarray(Xq[:, :3]))
+    else:
+        ref = go.MFGP(X4, y, MF2_PARAMS, F=2, gram=False)
+        mu, var = ref.predict(Xq)
+        mu, var = mu[:, 0], var[:, 0]
+        scale = float(MF2_PARAMS[0] * MF2_PARAMS[8] ** 2 + MF2_PARAMS[4])
+        what = "oracle.gp_oracle.MFGP.predict (emukit AR1 arithmetic restated, direct distances)"
+        mu_h, var_h = predict_api(Xq)
+    t_cpu = time.perf_counter() - t0
+    dm, dv = dmean.cpu().numpy()[idx], dvar.cpu().numpy()[idx]
+    nrm = lambda a, b, s: float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), s))
+    return {"n": int(idx.size), "against": what, "mode": args.mode,
+            "max_rel_mean": max(nrm(dm, mu, 0.0), nrm(mu_h[:, 0], mu, 0.0)),
+            "max_rel_var": max(nrm(dv, var, scale), nrm(var_h[:, 0], var, scale)),
+            "max_elem_rel_var": float(max(np.max(np.abs(dv - var) / var), np.max(np.abs(var_h[:, 0] - var) / var))),
+            "max_elem_rel_mean_floor_1e-3": float(np.max(np.abs(dm - mu) / np.maximum(np.abs(mu), 1e-3 * np.max(np.abs(mu))))),
+            "min_var": float(var.min()), "definition": "max_rel_* normwise: max|gpu - ref| / max(max|ref|, prior variance); "
+            "both the device-resident (value) and the host-buffer (e2e) results are checked", "oracle_s": t_cpu}
+
+
 NIGP_HYP = dict(ls=np.array([2.0, 3.0, 2.5]), sigma_f=4.0, sigma_y=0.2, sigma_x=np.array([0.1, 0.1, 0.05]))
 
 
@@ -441,6 +473,14 @@ def run_ours(args):
     if not (err_m <= 1e-9 * max(1.0, float(np.max(np.abs(dm)))) and err_v <= 1e-9 * MF2_PARAMS[0]):
         raise SystemExit("e2e and device-resident results disagree: mean %.3e var %.3e" % (err_m, err_v))
 
+    # ---- parity of what was just timed, against the CPU oracle (the checker, never the thing measured): a strided
+    # 4096-point sample of this rank's test set, device-resident (value) and host-buffer (e2e) results ------------
+    parity = None
+    if rank == 0 and args.parity:
+        parity = oracle_parity(args, X4, y, noise_diag, Xs4_host, dmean, dvar, predict_api, nigp_mode)
+        if not (parity["max_rel_mean"] <= 1e-9 and parity["max_rel_var"] <= 1e-9):
+            raise SystemExit("parity against the oracle failed: %s" % json.dumps(parity))
+
     # configs[2] also asks for the Xs_input_noise path (NIGP.py:304-324: + sum_d (d mean / d x_d)^2 sigma_x_d^2,
     # needs the mean gradients): one untimed and one timed call through the reference-facing API
     noisy = None
@@ -585,7 +625,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "mode": args.mode, "other_mode": other,
             "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast, "factor": factor,
-            "mean_only": mean_only, "noisy_input": noisy}
+            "mean_only": mean_only, "noisy_input": noisy, "parity": parity}
 
     if args.ig and not nigp_mode:
         line["ig"] = bench_ig(args, gpcore, L, torch, local)
@@ -674,6 +714,7 @@ def main():
     ap.add_argument("--n-train", type=int, default=0)
     ap.add_argument("--m-test", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--parity", type=int, default=1, help="check the timed results against the CPU oracle (4096 points)")
     ap.add_argument("--ig", type=int, default=1)
     ap.add_argument("--ig-candidates", type=int, default=65536)
     args = ap.parse_args()

@@ -158,3 +158,37 @@ def test_trainer_io_formats(tmp_path):
     tp = d["test_sub"]
     evaluate.write_gpres_csv(str(tmp_path / "GPRes.csv"), tp, tp[:, :1], tp[:, :1], tp[:, :1], tp[:, :1], tp[:, :1])
     assert np.loadtxt(tmp_path / "GPRes.csv", delimiter=",", skiprows=1).shape == (len(tp), 8)
+
+
+def test_parameter_transforms_softplus_and_logistic():
+    """optimize() works in GPy's raw spaces: Logexp (softplus) for positives, Logistic for ``constrain_bounded`` --
+    smooth, strictly inside the bounds, derivative consistent with the map (a clamp made the objective
+    flat past a bound while the gradient stayed non-zero)."""
+    from gpcore.gp_models import _transforms
+    lo = np.array([0.0, 1e-4, 0.0, 0.5])
+    hi = np.array([np.inf, 100.0, np.inf, 2.0])
+    from_raw, dth, to_raw = _transforms(lo, hi)
+    th0 = np.array([2.5, 3.0, 1e-3, 1.25])
+    x0 = to_raw(th0)
+    assert np.allclose(from_raw(x0), th0, rtol=1e-12, atol=0)
+    for x in (x0, x0 + 3.0, x0 - 5.0, np.array([40.0, 50.0, -30.0, -50.0])):
+        th = from_raw(x)
+        assert np.all(th[[1, 3]] >= lo[[1, 3]]) and np.all(th[[1, 3]] <= hi[[1, 3]]) and np.all(th > 0)
+        e = 1e-6
+        fd = (from_raw(x + e) - from_raw(x - e)) / (2 * e)
+        assert np.allclose(dth(th), fd, rtol=1e-5, atol=1e-12)
+    # a start on or outside a bound is moved strictly inside instead of producing an infinite raw value
+    assert np.all(np.isfinite(to_raw(np.array([1.0, 100.0, 1.0, 0.5]))))
+    assert np.all(np.isfinite(to_raw(np.array([1.0, 500.0, 1.0, 0.1]))))
+
+
+def test_multi_fidelity_rows_are_validated_on_the_host():
+    from gpcore.gp_models import _x4_mf
+    ok = np.array([[0.0, 1.0, 2.0, 1.0], [3.0, 4.0, 5.0, 0.0]])
+    assert _x4_mf(ok, 2) is ok
+    for bad in (2.0, -1.0, 0.5, np.nan):
+        X = ok.copy()
+        X[1, 3] = bad
+        with pytest.raises(ValueError, match="fidelity"):
+            _x4_mf(X, 2)
+    assert _x4_mf(np.array([[1.0, 2.0, 1.0]]), 3).shape == (1, 4)       # (x, y, fid) -> (x, y, 0, fid)

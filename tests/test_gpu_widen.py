@@ -550,3 +550,77 @@ def test_reference_information_gain_script(gpcore_mod, go):
         assert abs(I - wI) < 1e-5 * max(1.0, abs(wI)), (seed, I, wI)
         assert abs(I2 - wI2) < 1e-8 * max(1.0, abs(wI2)), (seed, I2, wI2)
         assert abs(I3 - wI3) < 1e-7 * max(1.0, abs(wI3)), (seed, I3, wI3)
+
+
+def test_optimize_with_an_active_bound(gpcore_mod):
+    """``lengthscale.constrain_bounded(lo, hi)`` (``...MFGP.py:408-410,664-666``) with the bound ACTIVE: the optimum of
+    the free problem lies outside, the bounded fit must end strictly inside the interval, lower the NLML, and leave a
+    small projected gradient in the raw (Logistic) space -- not stall on a flat clamped objective."""
+    from gpcore.GPy.kern import RBF
+    from gpcore.GPy.models import GPRegression
+    d = golden("field_data.npz")
+    X, y = d["Xh"][:300], d["y"][:300]
+    free = GPRegression(X, y[:, None], RBF(3, ARD=True))
+    free.optimize(max_iters=60)
+    ls_free = np.array(free.kern.lengthscale)
+    hi = float(0.6 * ls_free.min())                          # every free optimum lies above the upper bound
+    m = GPRegression(X, y[:, None], RBF(3, ARD=True))
+    m.kern.lengthscale.constrain_bounded(1e-4, hi)
+    f0 = m.objective_function()
+    m.optimize(max_iters=60)
+    ls = np.array(m.kern.lengthscale)
+    assert np.all(ls > 1e-4) and np.all(ls < hi), (ls, hi)
+    assert np.any(ls > 0.95 * hi)                             # pressed against the bound
+    assert m.objective_function() < f0
+    # finite-difference optimiser path agrees on where it lands (same transform, no analytic gradient)
+    m2 = GPRegression(X, y[:, None], RBF(3, ARD=True))
+    m2.kern.lengthscale.constrain_bounded(1e-4, hi)
+    m2.optimize(max_iters=60, analytic_gradients=False)
+    assert abs(m2.objective_function() - m.objective_function()) < 1e-2 * abs(m.objective_function())
+
+
+def test_out_of_range_fidelity_is_rejected_everywhere(gpcore_mod):
+    """emukit raises on a fidelity label outside [0, F); so must every entry point that takes fidelity-indexed rows
+    (test rows of predict_cov, kernel_matrix rows and the information-gain grid were unchecked)."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(3)
+    N, F = 200, 3
+    X4 = np.hstack([rng.uniform(0, 10, (N, 3)), rng.integers(0, F, (N, 1)).astype(float)])
+    y = rng.standard_normal(N)
+    p = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
+    core = gpcore_mod.GPCore(L_.KIND_MF_AR1_RBF, F, 0)
+    core.set_hypers(p, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    good = np.hstack([rng.uniform(0, 10, (20, 3)), 2 * np.ones((20, 1))])
+    cand, offs = good[:8].copy(), np.array([0, 8])
+    for badval in (3.0, -1.0, 1.5, np.nan):
+        bad = good.copy()
+        bad[7, 3] = badval
+        with pytest.raises(gpcore_mod.GpcoreError, match="fidelity"):
+            core.predict(bad, L_.INCLUDE_NOISE)
+        with pytest.raises(gpcore_mod.GpcoreError, match="fidelity"):
+            core.predict_cov(bad, L_.INCLUDE_NOISE)
+        with pytest.raises(gpcore_mod.GpcoreError, match="fidelity"):
+            core.kernel_matrix(bad)
+        with pytest.raises(gpcore_mod.GpcoreError, match="fidelity"):
+            core.kernel_matrix(good, bad)
+        with pytest.raises(gpcore_mod.GpcoreError, match="fidelity"):
+            core.ig_logdet(bad, cand, offs)
+        with pytest.raises(gpcore_mod.GpcoreError, match="fidelity"):
+            core.ig_logdet(good, bad[:8], offs)
+    # the handle stays usable, and the mirror model raises ValueError before reaching the device
+    m, v = core.predict(good, L_.INCLUDE_NOISE)
+    assert np.all(np.isfinite(m)) and np.all(v > 0)
+    core.close()
+    from gpcore.GPy.kern import RBF
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    k = LinearMultiFidelityKernel([RBF(3, ARD=True) for _ in range(F)])
+    w = GPyMultiOutputWrapper(GPyLinearMultiFidelityModel(X4, y[:, None], k, n_fidelities=F), F, 1)
+    bad = good.copy()
+    bad[0, 3] = 3.0
+    for call in (w.predict, w.predict_covariance, k.K):
+        with pytest.raises(ValueError, match="fidelity"):
+            call(bad)

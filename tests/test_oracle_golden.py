@@ -180,3 +180,40 @@ def test_getEID_host_logic_matches_reference():
     assert np.all(np.isfinite(E)) and abs(E.sum() - 1) < 1e-12 and ss.shape == (100, 3)
     E, _ = getEID(neg, g["WS"], float(g["mD"]))                    # simulation variant: uniform map
     assert np.allclose(E, 1.0 / E.shape[0])
+
+
+def test_scale_fixtures_were_generated_on_the_seeded_inputs():
+    """tests/golden/scale_oracle.npz and nigp_8192.npz freeze oracle / reference outputs at the BASELINE sizes; the GPU
+    tests use them only when the checksum of the regenerated inputs matches.  Check that it does (else those tests fall
+    back to minutes of live oracle work on the GPU box)."""
+    import hashlib
+    import scale_cases as sc
+    import bench
+    g = golden("scale_oracle.npz")
+    X4, y, p, Xs4 = sc.configs1_inputs()
+    assert str(g["c1_sha"]) == sc.sha(X4, y, p, Xs4)
+    X4, y, p, cands, grid4 = sc.configs3_inputs()
+    assert str(g["c3_sha"]) == sc.sha(X4, y, p, grid4, *cands)
+    X, y, p, Xs = sc.sf16384_inputs()
+    assert str(g["s16_sha"]) == sc.sha(X, y, p, Xs)
+    n = golden("nigp_8192.npz")
+    X4, y = bench.make_train(int(n["N"]), 3)
+    X = np.ascontiguousarray(X4[:, :3])
+    assert hashlib.sha256(X.tobytes() + y.tobytes()).hexdigest() == str(n["train_sha256"])
+    # the literal refit loop and the Schur form agree at N = 4096 as well (CPU vs CPU, frozen)
+    k = len(g["c3_seq_loop"])
+    assert normwise(g["c3_seq_schur"][:k], g["c3_seq_loop"], 1.0) < 1e-10
+
+
+def test_restated_nigp_fit_lands_on_the_reference_fit():
+    """oracle ``nigp_fit`` (NIGP.py:191-260 restated) against the reference's own fit (nigp_fit.npz), both distance
+    formulations, within 10 x the recorded CPU-vs-CPU spread."""
+    g = golden("nigp_fit.npz")
+    tol = max(1e-6, 10.0 * float(g["spread_params"]))
+    for gram in (True, False):
+        np.random.seed(0)
+        np.random.randn(40, 1)
+        np.random.randn(40)
+        p, _, nd, _ = go.nigp_fit(g["X"], g["y"], int(g["n_restarts"]), int(g["iters"]), int(g["maxiter_opt"]), gram=gram)
+        assert np.max(np.abs(p - g["params"]) / np.abs(g["params"])) < tol
+        assert normwise(nd, g["noise_diag"]) < 100 * tol

@@ -357,18 +357,14 @@ int ensure_slices(gpc_handle h) {
 double kstar_scale(gpc_handle h) {
   double kmax = 0.0;
   for (int i = 0; i < h->F; ++i) kmax = std::fmax(kmax, h->hyp.kdiag[i]);  // |k(a, b)| <= max prior variance
-  int e = 0;
-  std::frexp(kmax, &e);
-  return std::ldexp(1.0, e + 2);  // |k| / sA < 1/4
+  return kmax > 0.0 ? kmax * gpoz::SCALE_HEADROOM : 1.0;  // |k| / sA <= 0.4975 (Cauchy-Schwarz: |k(a, b)| <= max prior variance)
 }
 
 // Scale of the digits of V = L^-1 K*: sum_i V_i^2 <= k(x*, x*), so |V| <= sqrt(max prior variance).
 double v_scale(gpc_handle h) {
   double kmax = 0.0;
   for (int i = 0; i < h->F; ++i) kmax = std::fmax(kmax, h->hyp.kdiag[i]);
-  int e = 0;
-  std::frexp(std::sqrt(kmax), &e);
-  return std::ldexp(1.0, e + 2);  // |V| / sV < 1/4
+  return kmax > 0.0 ? std::sqrt(kmax) * gpoz::SCALE_HEADROOM : 1.0;  // |V| / sV <= 0.4975
 }
 
 template <int OUT, bool FULLK>

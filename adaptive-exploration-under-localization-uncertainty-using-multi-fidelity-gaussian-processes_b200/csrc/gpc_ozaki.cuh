@@ -6,8 +6,10 @@
 // (4.56 POP/s measured, profiles/r01/umma_i8_rate_r01.txt) with the Ozaki splitting scheme:
 //
 //   x = scale * 2^-48 * v,  v = rint(x / scale * 2^48) = sum_{p<S} d_p 256^(S-1-p),  d_p in [-128, 127]
-//   (balanced base-256 digits, S = 6 int8 "slices" per operand; with |x| / scale < 1/4 the bytes of
-//   v + 0x808080808080 are the digits + 128, so slicing is one add and byte permutes), so that
+//   (balanced base-256 digits, S = 6 int8 "slices" per operand; the balanced range is
+//   [-0.50196, 0.49804] 2^48, so with |x| / scale <= 0.4975 the bytes of v + 0x808080808080 are the digits + 128 and
+//   slicing is one add and byte permutes.  Scales are NOT rounded to powers of two: every factor of two of headroom
+//   costs one bit of the result -- the terms dropped below carry 2^-45 sA sB), so that
 //   sum_k a_k b_k = sA sB 2^-96 sum_{p,q} 256^(10-p-q) sum_k d^A_pk d^B_qk.
 // Every digit GEMM C_pq = D^A_p (D^B_q)^T is exact in int32 (|d| <= 128, up to 6 pairs per
 // accumulator: K <= 21845); the pairs with p + q = t share one TMEM accumulator; pairs with
@@ -45,6 +47,7 @@ constexpr int STAGE_BYTES = A_STAGE + B_STAGE;   // 73728
 constexpr int STAGES = 3;
 constexpr int MAX_K = 16384;         // int32 accumulators: 6 pairs x K x 128^2 < 2^31
 constexpr double DIGIT_MUL = 281474976710656.0;           // 2^48
+constexpr double SCALE_HEADROOM = 1.0 / 0.4975;           // scale = max|x| * this: |v| <= 0.4975 2^48, inside the balanced range
 constexpr long long DIGIT_BIAS = 0x808080808080LL;        // 128 (256^6 - 1) / 255
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 constexpr int NT = 192;
@@ -127,7 +130,7 @@ __device__ __forceinline__ uint4 pack_slice(const unsigned long long (&u)[16], i
 
 // ------------------------------------------------------------------------------------------
 // Digits of the rows of X = L^-1 (lower triangular, row-major, ld).  Row i is scaled by
-// sB[i] = 2^e with |X(i, :)| / sB[i] <= 1/4.  One warp per row; grid = nrows / 8, 256 threads.  tri = 0: general rows
+// sB[i] = max|X(i, :)| / 0.4975.  One warp per row; grid = nrows / 8, 256 threads.  tri = 0: general rows
 // (the grid's V for the cross products of the information gain).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X, long ld, long n_pad,
@@ -143,9 +146,7 @@ __global__ void __launch_bounds__(256) k_slice_rows(const double* __restrict__ X
   for (long k = lane; k <= klast; k += 32) mx = fmax(mx, fabs(row[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  int e = 0;
-  frexp(mx, &e);  // mx = f 2^e, f in [0.5, 1)  ->  |x| / 2^(e+2) < 1/4: the top balanced digit cannot overflow
-  const double scale = (mx > 0.0) ? ldexp(1.0, e + 2) : 1.0;
+  const double scale = (mx > 0.0) ? mx * SCALE_HEADROOM : 1.0;   // the top balanced digit cannot overflow
   if (lane == 0) sB[i] = scale;
   const double mul = DIGIT_MUL / scale;
   const long jb = i >> 6, r = i & 63;

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,7 +20,36 @@
 
 #define GPC_VERSION 100
 
+// flag |= 1 when a row's fidelity label is not an integer in [0, F) (multi-fidelity models; emukit raises there)
+__global__ void __launch_bounds__(256) k_check_fid(const double* __restrict__ X4, long M, int F, int* __restrict__ flag) {
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= M) return;
+  const double f = X4[i * 4 + 3];
+  if (!(f >= 0.0) || f >= (double)F || f != floor(f)) atomicOr(flag, 1);
+}
+
 namespace {
+
+// Page-locked host staging memory (cudaHostAlloc): the bounce buffers of gpc_predict for pageable caller arrays.
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  double* d() const { return static_cast<double*>(p); }
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -68,6 +98,7 @@ struct gpc_handle_s {
   bool have_extra = false;
   // prediction workspaces
   DevBuf Xs4, Kx, meanpart, sumsq, gradpart, mean, var, Vt, cov, grads, ediag;
+  PinBuf pin_in, pin_sx, pin_mean, pin_var;   // gpc_predict: page-locked staging of pageable caller arrays (2 stages each)
   // tcgen05 / INT8 path (gpc_ozaki.cuh): digit images of L^-1 and of the current K* chunk
   DevBuf Bimg, sBv, Aimg, Aimg2, meanpart2, gradpart2;
   cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_v[2] = {nullptr, nullptr};
@@ -484,13 +515,18 @@ int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean,
     CK(Mb[b]->ensure((size_t)nchunks * mp_max * 8));
     if (d_sx) CK(Gb[b]->ensure((size_t)nchunks * 3 * mp_max * 8));
   }
-  CK(h->sumsq.ensure((size_t)(2 * h->nb) * mp_max * 8));
+  CK(h->sumsq.ensure((size_t)(4 * h->nb) * mp_max * 8));   // k_vt_i8 leaves two partial sums per 64-column tile
   // the assembly runs on the LOW-priority stream: when k_vt_i8 of chunk i and the assembly of chunk i+1 become
   // runnable together, the contraction's persistent CTAs are placed first and the assembly fills in behind them
   cudaStream_t s1 = h->stream, s2 = h->inv;
   CK(cudaEventRecord(h->ev_main, s1));       // the side stream starts after everything queued so far
   CK(cudaStreamWaitEvent(s2, h->ev_main, 0));
   const double sA = kstar_scale(h);
+  // profiling only (profiles/tools/phase_power.py): GPC_I8_PHASE=kstar / vt runs one of the two kernels of the pipeline
+  // alone (results are then meaningless) so that clocks and board power can be sampled per kernel
+  const char* phase_env = std::getenv("GPC_I8_PHASE");
+  const bool run_kstar = !phase_env || std::strcmp(phase_env, "vt") != 0;
+  const bool run_vt = !phase_env || std::strcmp(phase_env, "kstar") != 0;
   long i = 0;
   for (long o = 0; o < M; o += mc, ++i) {
     const long m = (M - o) < mc ? (M - o) : mc;
@@ -499,7 +535,8 @@ int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean,
     const double* xs = dXs4 + o * 4;
     if (i >= 2) CK(cudaStreamWaitEvent(s2, h->ev_v[b], 0));  // chunk i-2 no longer reads this buffer
     const dim3 grid((unsigned)(m_pad / 128), (unsigned)nchunks);
-    if (d_sx)
+    if (!run_kstar) {
+    } else if (d_sx)
       k_kstar_i8<true><<<grid, 128, 0, s2>>>(h->hyp, h->Xt.d(), h->alpha.d(), h->N, np, xs, m, m_pad, sA,
                                              static_cast<int8_t*>(Ab[b]->p), Mb[b]->d(), Gb[b]->d());
     else
@@ -508,9 +545,9 @@ int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean,
     CKL();
     CK(cudaEventRecord(h->ev_k[b], s2));
     CK(cudaStreamWaitEvent(s1, h->ev_k[b], 0));
-    if ((rc = launch_vt_i8<OUT_SUMSQ>(h, static_cast<const int8_t*>(Ab[b]->p), m_pad, nullptr, h->sumsq.d()))) return rc;
+    if (run_vt && (rc = launch_vt_i8<OUT_SUMSQ>(h, static_cast<const int8_t*>(Ab[b]->p), m_pad, nullptr, h->sumsq.d()))) return rc;
     k_finalize_pred<<<(unsigned)((m + 255) / 256), 256, 0, s1>>>(
-        h->hyp, xs, m, m_pad, Mb[b]->d(), nchunks, h->sumsq.d(), 2 * h->nb, Gb[b]->d(),
+        h->hyp, xs, m, m_pad, Mb[b]->d(), nchunks, h->sumsq.d(), 4 * h->nb, Gb[b]->d(),
         d_sx ? d_sx + (sx_rows == 1 ? 0 : o * 3) : nullptr, sx_rows, dmean ? dmean + o : nullptr, dvar + o, flags);
     CKL();
     CK(cudaEventRecord(h->ev_v[b], s1));
@@ -639,6 +676,7 @@ int gpc_destroy(gpc_handle h) {
                     &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->Aimg2, &h->meanpart2, &h->gradpart2, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
+  h->pin_in.release(); h->pin_sx.release(); h->pin_mean.release(); h->pin_var.release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
@@ -977,11 +1015,27 @@ int gpc_predict_dev(gpc_handle h, const double* dXs4, long M, double* dmean, dou
   return predict_rows(h, dXs4, M, dmean, dvar, flags, nullptr, 0);
 }
 
-// Host-pointer posterior: the test rows are copied to the device in "super-chunks" of up to
-// GPC_STAGE_ROWS rows (one H2D copy, m_chunk-row launches back to back with no host sync in
-// between, one D2H copy per output), so copies and kernels queue up on the stream instead of
-// ping-ponging with the host once per launch.
-#define GPC_STAGE_ROWS (1L << 18)
+// Host-pointer posterior.  The test rows travel in stages of up to GPC_STAGE_ROWS rows; two device stages alternate.
+// The copy stream (in order) carries  in(0), in(1), out(0), in(2), out(1), ...: the host -> device copy of stage s + 1
+// and the device -> host copy of stage s - 1 run while the compute stream works on stage s.
+//
+// Caller arrays are usually PAGEABLE (plain NumPy arrays): a cudaMemcpyAsync on pageable memory blocks the host (for a
+// device -> host copy until the data has arrived), which would serialise the pipeline.  So pageable arrays are staged
+// through the handle's own page-locked buffers: the host thread memcpy's stage s + 1 into its pinned input buffer and
+// drains the pinned results of stage s - 1 into the caller's arrays while the GPU computes stage s; every copy the GPU
+// sees is a plain cudaMemcpyAsync on pinned memory.  Arrays the caller has pinned itself (cudaHostAlloc /
+// cudaHostRegister, detected with cudaPointerGetAttributes) are used in place.
+#define GPC_STAGE_ROWS (1L << 17)
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int predict_host(gpc_handle h, const double* Xs4, long M, const double* sx, long sx_rows, double* mean,
                         double* var, unsigned flags) {
   int rc = require_factor(h);
@@ -991,11 +1045,7 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
   if (sx && (h->F != 1 || h->hyp.base != 0))
     return fail(h, GPC_ERR_ARG, "input-noise correction is defined for the single-fidelity squared-exponential kernel");
   if (M == 0) return GPC_OK;
-  if ((rc = check_fidelity_rows(h, Xs4, M, "test rows"))) return rc;
   CK(cudaSetDevice(h->device));
-  // Two device stages alternate.  The copy stream (in order) carries  in(0), in(1), out(0), in(2), out(1), ... : the
-  // host -> device copy of stage s + 1 and the device -> host copy of stage s - 1 run while the compute stream works
-  // on stage s; the host synchronises once, at the end.
   const long stage = M <= GPC_STAGE_ROWS ? round_up(M, 128) : GPC_STAGE_ROWS;
   const int nbuf = M > stage ? 2 : 1;
   CK(h->Xs4.ensure((size_t)nbuf * stage * 32));
@@ -1003,23 +1053,70 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
   CK(h->var.ensure((size_t)nbuf * stage * 8));
   cudaStream_t sc = h->stream, sio = h->side;
   const bool per_row_sx = sx && sx_rows != 1;
+  const bool want_var = var && !(flags & GPC_MEAN_ONLY);
+  const bool stage_in = !is_pinned(Xs4) || (per_row_sx && !is_pinned(sx));
+  const bool stage_out = !is_pinned(mean) || (want_var && !is_pinned(var));
+  if (stage_in) {
+    CK(h->pin_in.ensure((size_t)nbuf * stage * 32));
+    if (per_row_sx) CK(h->pin_sx.ensure((size_t)nbuf * stage * 24));
+  }
+  if (stage_out) {
+    if (mean) CK(h->pin_mean.ensure((size_t)nbuf * stage * 8));
+    if (want_var) CK(h->pin_var.ensure((size_t)nbuf * stage * 8));
+  }
   if (sx) {
     CK(h->ediag.ensure((size_t)(per_row_sx ? nbuf * stage : 1) * 24));
     if (!per_row_sx) CK(cudaMemcpyAsync(h->ediag.p, sx, 24, cudaMemcpyHostToDevice, sc));
   }
-  const bool want_var = var && !(flags & GPC_MEAN_ONLY);
+  int* d_badfid = static_cast<int*>(h->status.p) + 4;
+  CK(cudaMemsetAsync(d_badfid, 0, sizeof(int), sc));
   CK(cudaEventRecord(h->ev_cmp[0], sc));            // the copy stream starts behind everything queued so far
   CK(cudaStreamWaitEvent(sio, h->ev_cmp[0], 0));
+  const long nstage = (M + stage - 1) / stage;
+  // any error below leaves copies into caller-owned memory in flight: quiesce both streams before returning
+  auto bail = [&](int code) {
+    cudaStreamSynchronize(sio);
+    cudaStreamSynchronize(sc);
+    return code;
+  };
+#define CKB(call)                                                                                            \
+  do {                                                                                                      \
+    cudaError_t e__ = (call);                                                                               \
+    if (e__ != cudaSuccess) return bail(fail(h, GPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__))); \
+  } while (0)
   auto copy_in = [&](long si) -> int {
     const long s0 = si * stage, ms = (M - s0) < stage ? (M - s0) : stage;
     const int b = (int)(si % nbuf);
-    CK(cudaMemcpyAsync(h->Xs4.d() + (size_t)b * stage * 4, Xs4 + s0 * 4, (size_t)ms * 32, cudaMemcpyHostToDevice, sio));
+    const double* src = Xs4 + s0 * 4;
+    const double* srcx = per_row_sx ? sx + s0 * 3 : nullptr;
+    if (stage_in) {
+      // the pinned buffer last fed stage si - 2: that copy completed long ago, but make it explicit
+      if (si >= 2) CKB(cudaEventSynchronize(h->ev_h2d[b]));
+      double* pin = h->pin_in.d() + (size_t)b * stage * 4;
+      std::memcpy(pin, src, (size_t)ms * 32);
+      src = pin;
+      if (per_row_sx) {
+        double* pinx = h->pin_sx.d() + (size_t)b * stage * 3;
+        std::memcpy(pinx, srcx, (size_t)ms * 24);
+        srcx = pinx;
+      }
+    }
+    CKB(cudaMemcpyAsync(h->Xs4.d() + (size_t)b * stage * 4, src, (size_t)ms * 32, cudaMemcpyHostToDevice, sio));
     if (per_row_sx)
-      CK(cudaMemcpyAsync(h->ediag.d() + (size_t)b * stage * 3, sx + s0 * 3, (size_t)ms * 24, cudaMemcpyHostToDevice, sio));
-    CK(cudaEventRecord(h->ev_h2d[b], sio));
+      CKB(cudaMemcpyAsync(h->ediag.d() + (size_t)b * stage * 3, srcx, (size_t)ms * 24, cudaMemcpyHostToDevice, sio));
+    CKB(cudaEventRecord(h->ev_h2d[b], sio));
     return GPC_OK;
   };
-  const long nstage = (M + stage - 1) / stage;
+  // results of stage si: pinned bounce buffer -> caller arrays, once its device -> host copy has completed
+  auto drain = [&](long si) -> int {
+    if (!stage_out) return GPC_OK;
+    const long s0 = si * stage, ms = (M - s0) < stage ? (M - s0) : stage;
+    const int b = (int)(si % nbuf);
+    CKB(cudaEventSynchronize(h->ev_d2h[b]));
+    if (mean) std::memcpy(mean + s0, h->pin_mean.d() + (size_t)b * stage, (size_t)ms * 8);
+    if (want_var) std::memcpy(var + s0, h->pin_var.d() + (size_t)b * stage, (size_t)ms * 8);
+    return GPC_OK;
+  };
   if ((rc = copy_in(0))) return rc;
   for (long si = 0; si < nstage; ++si) {
     const long s0 = si * stage, ms = (M - s0) < stage ? (M - s0) : stage;
@@ -1028,18 +1125,30 @@ static int predict_host(gpc_handle h, const double* Xs4, long M, const double* s
     double* dm = h->mean.d() + (size_t)b * stage;
     double* dv = h->var.d() + (size_t)b * stage;
     const double* de = sx ? (per_row_sx ? h->ediag.d() + (size_t)b * stage * 3 : h->ediag.d()) : nullptr;
-    CK(cudaStreamWaitEvent(sc, h->ev_h2d[b], 0));                       // inputs of this stage have landed
-    if (si >= 2) CK(cudaStreamWaitEvent(sc, h->ev_d2h[b], 0));          // results of stage s - 2 have left these buffers
-    if ((rc = predict_rows(h, dX, ms, mean ? dm : nullptr, want_var ? dv : nullptr, flags, de, sx_rows))) return rc;
-    CK(cudaEventRecord(h->ev_cmp[b], sc));
+    CKB(cudaStreamWaitEvent(sc, h->ev_h2d[b], 0));                       // inputs of this stage have landed
+    if (si >= 2) CKB(cudaStreamWaitEvent(sc, h->ev_d2h[b], 0));          // results of stage s - 2 have left these buffers
+    if (h->F > 1) {
+      k_check_fid<<<(unsigned)((ms + 255) / 256), 256, 0, sc>>>(dX, ms, h->F, d_badfid);
+      ++h->launches;
+    }
+    if ((rc = predict_rows(h, dX, ms, mean ? dm : nullptr, want_var ? dv : nullptr, flags, de, sx_rows))) return bail(rc);
+    CKB(cudaEventRecord(h->ev_cmp[b], sc));
     if (si + 1 < nstage && (rc = copy_in(si + 1))) return rc;           // queued BEFORE out(s): it must not wait for compute(s)
-    CK(cudaStreamWaitEvent(sio, h->ev_cmp[b], 0));
-    if (mean) CK(cudaMemcpyAsync(mean + s0, dm, (size_t)ms * 8, cudaMemcpyDeviceToHost, sio));
-    if (want_var) CK(cudaMemcpyAsync(var + s0, dv, (size_t)ms * 8, cudaMemcpyDeviceToHost, sio));
-    CK(cudaEventRecord(h->ev_d2h[b], sio));
+    CKB(cudaStreamWaitEvent(sio, h->ev_cmp[b], 0));
+    double* om = stage_out ? h->pin_mean.d() + (size_t)b * stage : mean + s0;
+    double* ov = stage_out ? h->pin_var.d() + (size_t)b * stage : var + s0;
+    if (mean) CKB(cudaMemcpyAsync(om, dm, (size_t)ms * 8, cudaMemcpyDeviceToHost, sio));
+    if (want_var) CKB(cudaMemcpyAsync(ov, dv, (size_t)ms * 8, cudaMemcpyDeviceToHost, sio));
+    CKB(cudaEventRecord(h->ev_d2h[b], sio));
+    if (si >= 1 && (rc = drain(si - 1))) return rc;                     // while the GPU computes stage si
   }
-  CK(cudaStreamSynchronize(sio));
-  CK(cudaStreamSynchronize(sc));
+  if ((rc = drain(nstage - 1))) return rc;
+  int badfid = 0;
+  CKB(cudaMemcpyAsync(&badfid, d_badfid, sizeof(int), cudaMemcpyDeviceToHost, sc));
+  CKB(cudaStreamSynchronize(sio));
+  CKB(cudaStreamSynchronize(sc));
+#undef CKB
+  if (badfid) return fail(h, GPC_ERR_ARG, "test rows: fidelity index must be an integer in [0, F)");
   return GPC_OK;
 }
 

@@ -23,11 +23,11 @@
 //   A image  [m_pad/128][n_pad/64][S][8 KB]   test rows  x train index (digits of K* / sA)
 //   B image  [n_pad/64 ][n_pad/64][S][4 KB]   rows of X x train index (digits of X_i,: / sB_i)
 //
-// Kernel k_vt_i8: persistent, one CTA per SM, 192 threads:
+// Kernel k_vt_i8: persistent, one CTA per SM, 320 threads:
 //   warp 0   TMA producer (one lane): 3-stage ring of (A k-block, B k-block) = 72 KB per stage
 //   warp 1   MMA issuer (one lane): 16 tcgen05.mma.kind::i8 (M = 128, N = 64..256, K = 32) per stage into
 //            S accumulators of 64 TMEM columns; tcgen05.commit frees the stage / publishes the tile
-//   warps 2-5 epilogue: tcgen05.ld the S int32 levels (software-pipelined), recombine in int64, scale to FP64 and
+//   warps 2-9 epilogue (two per TMEM lane quarter, 32 columns each): tcgen05.ld the S int32 levels (software-pipelined), recombine in int64, scale to FP64 and
 //            reduce sum_i V(n, i)^2 per test row (one thread owns a row: no shuffles), store V, or emit V's own
 //            digit image for the next INT8 product (information gain).
 // Schedules: triangular -- item (mt, p) = train tiles nb2-1-p then p of test tile mt (V = K* X^T, X lower
@@ -50,7 +50,7 @@ constexpr double DIGIT_MUL = 281474976710656.0;           // 2^48
 constexpr double SCALE_HEADROOM = 1.0 / 0.4975;           // scale = max|x| * this: |v| <= 0.4975 2^48, inside the balanced range
 constexpr long long DIGIT_BIAS = 0x808080808080LL;        // 128 (256^6 - 1) / 255
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
-constexpr int NT = 192;
+constexpr int NT = 320;               // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr double COMB_SCALE = 1.0 / 72057594037927936.0;  // 2^-56
 
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
 }
 
 // ------------------------------------------------------------------------------------------
-// The contraction.  grid = min(#SMs, items), 192 threads, dynamic smem gpoz::SMEM_BYTES.
+// The contraction.  grid = min(#SMs, items), 320 threads, dynamic smem gpoz::SMEM_BYTES.
 //   D(test tile mt, B row tile jb) = sum_kb A[mt][kb] B[jb][kb]^T  as 21 exact digit GEMMs.
 // Schedules:  triangular (FULLK = false): item (mt, p) = B tiles nb2-1-p then p, k-blocks 0..jb (V = K* X^T with
 //             X = L^-1 lower triangular; every item has nb2 + 1 k-steps);
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
-    mbar_init(&tmem_empty_bar, 4);  // one arrive per epilogue warp
+    mbar_init(&tmem_empty_bar, 8);  // one arrive per epilogue warp
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -471,14 +471,17 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4, one thread owns one test row =====
+    // ===== epilogue warps (2..9): TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; one thread owns one
+    // test row of one 32-column half of the tile =====
     // The MMA issuer cannot start the next tile before the accumulators are drained (6 x 64 of the 512
-    // TMEM columns: no room for a second set), so this loop is on the critical path: the row scales are
-    // staged while the MMAs still run, the TMEM loads of the next half-group are in flight during the
-    // arithmetic of the current one, and the accumulators are released right after the last load.
+    // TMEM columns: no room for a second set), so this loop is on the critical path: two warps per lane quarter
+    // halve it, the row scales are staged while the MMAs still run, the TMEM loads of the next half-group are in
+    // flight during the arithmetic of the current one, and the accumulators are released right after the last load.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const int et = tid - 64;
+    const int cbeg = half * (TN / 2), cend = cbeg + TN / 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const double cs = COMB_SCALE * sA;
     uint32_t tile = 0;
@@ -489,17 +492,17 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
         const int jb = jbs[sg];
         double* sbt = sb_tile[tile & 1];
         if (et < TN) sbt[et] = sB[(long)jb * TN + et] * cs;   // V = comb 2^-56 sA sB[i]
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait_guarded(&tmem_full_bar, tile & 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
         double ss = 0.0;
         const long n = (long)mt * TM + row;
         int32_t v0[8], v1[8], v2[8], w0[8], w1[8], w2[8];
-        tmem_ld8(lane_addr + 0 * TN, v0);
-        tmem_ld8(lane_addr + 1 * TN, v1);
-        tmem_ld8(lane_addr + 2 * TN, v2);
+        tmem_ld8(lane_addr + 0 * TN + cbeg, v0);
+        tmem_ld8(lane_addr + 1 * TN + cbeg, v1);
+        tmem_ld8(lane_addr + 2 * TN + cbeg, v2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 8) {
+        for (int c0 = cbeg; c0 < cend; c0 += 8) {
           tmem_wait3(v0, v1, v2);
           tmem_ld8(lane_addr + 3 * TN + c0, w0);
           tmem_ld8(lane_addr + 4 * TN + c0, w1);
@@ -508,12 +511,12 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
 #pragma unroll
           for (int j = 0; j < 8; ++j) hi[j] = (long long)v0[j] * 65536LL + (long long)v1[j] * 256LL + (long long)v2[j];
           tmem_wait3(w0, w1, w2);
-          if (c0 + 8 < TN) {
+          if (c0 + 8 < cend) {
             tmem_ld8(lane_addr + 0 * TN + c0 + 8, v0);
             tmem_ld8(lane_addr + 1 * TN + c0 + 8, v1);
             tmem_ld8(lane_addr + 2 * TN + c0 + 8, v2);
           } else {
-            // every accumulator of this tile has been read: hand TMEM back to the MMA issuer
+            // every accumulator column of this warp has been read: hand TMEM back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar);
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
             *reinterpret_cast<uint2*>(dst + 5L * A_SLICE) = pack_bytes8<0>(dv);
           }
         }
-        if (OUT == OUT_SUMSQ) a.sumsq[(long)jb * m_pad + n] = ss;
+        if (OUT == OUT_SUMSQ) a.sumsq[((long)jb * 2 + half) * m_pad + n] = ss;   // two partial sums per 64-column tile
       }
     }
   }

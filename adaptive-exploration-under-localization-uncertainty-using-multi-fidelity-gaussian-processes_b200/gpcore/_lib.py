@@ -29,6 +29,10 @@ class GpcoreError(RuntimeError):
     """Any non-OK status other than "not positive definite"."""
 
 
+class GpcoreArgError(GpcoreError, ValueError):
+    """``GPC_ERR_ARG`` (e.g. a fidelity label outside [0, F)): also a ``ValueError``, which is what emukit raises."""
+
+
 def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
 
@@ -148,4 +152,6 @@ def check(lib, handle, rc):
         raise np.linalg.LinAlgError(msg or "matrix is not positive definite")
     if rc == GPC_ERR_SHAPE:
         raise ValueError(msg)
+    if rc == GPC_ERR_ARG:
+        raise GpcoreArgError("gpcore status %d: %s" % (rc, msg))
     raise GpcoreError("gpcore status %d: %s" % (rc, msg))

@@ -254,6 +254,9 @@ def _kernel_core(kind, F, device):
     return core
 
 
+_HOST_CHECK_ROWS = 1 << 16   # larger inputs are validated on the device (gpc_predict: GpcoreArgError, a ValueError)
+
+
 def _x4_mf(X, n_fidelities=None):
     """(n, D + 1) rows with the fidelity index last -> (n, 4) rows; 3-D inputs already have the
     device row layout (x, y, z, fid) and pass through without a copy.  With ``n_fidelities`` the labels are
@@ -261,7 +264,7 @@ def _x4_mf(X, n_fidelities=None):
     X = np.asarray(X, dtype=float)
     if X.ndim != 2 or X.shape[1] < 2:
         raise ValueError("multi-fidelity inputs are (n, D + 1) rows with the fidelity index in the last column")
-    if n_fidelities is not None and X.shape[0]:
+    if n_fidelities is not None and 0 < X.shape[0] <= _HOST_CHECK_ROWS:
         f = X[:, -1]
         if not (np.all(f >= 0) and np.all(f < n_fidelities) and np.all(f == np.floor(f))):
             raise ValueError("fidelity index (last input column) must be an integer in [0, %d)" % n_fidelities)

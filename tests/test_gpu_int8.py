@@ -178,8 +178,9 @@ def test_int8_size_limit_and_fallback(gpcore_mod):
 
 
 def test_host_predict_stages(gpcore_mod, go):
-    """gpc_predict on host buffers longer than one device stage (2^18 rows): two alternating stages with the copies on
-    a second stream.  A ragged 600001-row call must equal the same rows predicted in small independent calls."""
+    """gpc_predict on host buffers longer than one device stage (2^17 rows): two alternating stages with the copies on
+    a second stream, pageable caller arrays staged through the handle's pinned ring.  A ragged 600001-row call must
+    equal the same rows predicted in small independent calls, and the same call on an input the caller pinned."""
     L_ = gpcore_mod._lib
     rng = np.random.default_rng(8)
     X4, y = synth(rng, 300, 1)
@@ -191,8 +192,12 @@ def test_host_predict_stages(gpcore_mod, go):
     Xs4 = np.hstack([rng.uniform(0, 10, (M, 3)), np.zeros((M, 1))])
     flags = L_.INCLUDE_NOISE | L_.CLIP_DIAG
     m, v = core.predict(Xs4, flags)
-    probes = [0, 1, 262143, 262144, 262145, 524287, 524288, 599999, 600000]
-    for lo in (0, 262000, 524000, 599000):
+    import torch
+    Xp = torch.from_numpy(Xs4).pin_memory().numpy()                    # caller-pinned input: used in place
+    mp, vp = core.predict(Xp, flags)
+    assert np.array_equal(m, mp) and np.array_equal(v, vp)
+    probes = [0, 1, 131071, 131072, 131073, 262143, 262144, 262145, 524287, 524288, 599999, 600000]
+    for lo in (0, 130500, 262000, 524000, 599000):
         hi = min(M, lo + 1001)
         m0, v0 = core.predict(np.ascontiguousarray(Xs4[lo:hi]), flags)
         assert np.array_equal(m[lo:hi], m0) and np.array_equal(v[lo:hi], v0), lo

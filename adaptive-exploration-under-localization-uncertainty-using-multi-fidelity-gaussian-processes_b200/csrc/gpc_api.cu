@@ -102,6 +102,8 @@ struct gpc_handle_s {
   // tcgen05 / INT8 path (gpc_ozaki.cuh): digit images of L^-1 and of the current K* chunk
   DevBuf Bimg, sBv, Aimg, Aimg2, meanpart2, gradpart2;
   cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_v[2] = {nullptr, nullptr};
+  cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;   // device time of the last information-gain call
+  double last_call_ms = 0.0;
   bool have_slices = false;
   int mode = GPC_MODE_INT8;
   int n_sm = 0;
@@ -689,6 +691,8 @@ int gpc_destroy(gpc_handle h) {
     if (h->ev_cmp[i]) cudaEventDestroy(h->ev_cmp[i]);
     if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
   }
+  if (h->ev_call0) cudaEventDestroy(h->ev_call0);
+  if (h->ev_call1) cudaEventDestroy(h->ev_call1);
   if (h->ev_half) cudaEventDestroy(h->ev_half);
   if (h->ev_inv) cudaEventDestroy(h->ev_inv);
   if (h->side) cudaStreamDestroy(h->side);
@@ -1427,6 +1431,12 @@ int gpc_set_chunk(gpc_handle h, long m_chunk) {
 int gpc_enable_hot_timing(gpc_handle h, int on) {
   if (!h) return GPC_ERR_ARG;
   h->hot_timing = on != 0;
+  return GPC_OK;
+}
+
+int gpc_last_call_device_ms(gpc_handle h, double* ms) {
+  if (!h || !ms) return GPC_ERR_ARG;
+  *ms = h->last_call_ms;
   return GPC_OK;
 }
 

@@ -100,6 +100,7 @@ SIGNATURES = {
     "gpc_set_chunk": (C.c_int, [_h, C.c_long]),
     "gpc_hot_kernel_time": (C.c_int, [_h, _dp, _lp, _dp, C.c_int]),
     "gpc_enable_hot_timing": (C.c_int, [_h, C.c_int]),
+    "gpc_last_call_device_ms": (C.c_int, [_h, _dp]),
 }
 
 _lib = None

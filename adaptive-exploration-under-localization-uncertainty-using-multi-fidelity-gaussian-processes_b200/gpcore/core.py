@@ -249,6 +249,12 @@ class GPCore:
     def enable_hot_timing(self, on=True):
         self._ck(self.lib.gpc_enable_hot_timing(self.h, int(bool(on))))
 
+    def last_call_device_ms(self):
+        """Device time (CUDA events) of the most recent information-gain call."""
+        ms = C.c_double()
+        self._ck(self.lib.gpc_last_call_device_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def hot_kernel_time(self, reset=False):
         ms, n, fl = C.c_double(), C.c_long(), C.c_double()
         self._ck(self.lib.gpc_hot_kernel_time(self.h, C.byref(ms), C.byref(n), C.byref(fl), int(reset)))

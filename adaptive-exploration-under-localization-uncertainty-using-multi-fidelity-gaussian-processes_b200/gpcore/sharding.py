@@ -45,10 +45,56 @@ def reduce_best(local_best_value, local_best_index, index_offset, group=None):
     return best_v, best_i
 
 
-def broadcast_factor(core, src=0, group=None):
+def trapezoids(n_pad, groups=8, block=128):
+    """Cover the lower block-triangle of an n_pad x n_pad matrix with ``groups`` row bands [r0, r1) x [0, r1): what
+    ``broadcast_factor`` sends instead of the full squares (the upper triangles of L and L^-1 are zeros).  Bands are
+    multiples of ``block`` rows; returns [(r0, r1), ...] and the fraction of n_pad^2 they hold (0.5 + 0.5 / groups)."""
+    nb = int(n_pad) // block
+    groups = max(1, min(int(groups), nb))
+    cuts = [round(g * nb / groups) * block for g in range(groups + 1)]
+    bands = [(cuts[g], cuts[g + 1]) for g in range(groups) if cuts[g + 1] > cuts[g]]
+    frac = sum((r1 - r0) * r1 for r0, r1 in bands) / float(n_pad * n_pad)
+    return bands, frac
+
+
+def broadcast_lower(t2d, src=0, group=None, groups=8):
+    """Broadcast the lower block-triangle of the square tensor ``t2d`` (any backend) band by band: the band is packed
+    into a contiguous buffer, broadcast, and written back on the receivers.  Returns the bytes broadcast."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    n = t2d.shape[0]
+    bands, _ = trapezoids(n, groups)
+    sent = 0
+    for r0, r1 in bands:
+        view = t2d[r0:r1, :r1]
+        buf = view.contiguous() if rank == src else torch.empty((r1 - r0, r1), dtype=t2d.dtype, device=t2d.device)
+        dist.broadcast(buf, src, group=group)
+        if rank != src:
+            view.copy_(buf)
+        sent += buf.numel() * buf.element_size()
+    return sent
+
+
+def warm_up(group=None):
+    """Create the communicator before anything is timed: the first NCCL collective of a process group pays for the
+    communicator set-up (~1 s at 8 ranks), which is not part of any factor broadcast."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.ones(1, device=dev)
+    dist.all_reduce(t, group=group)
+    dist.broadcast(t, 0, group=group)
+    if dev != "cpu":
+        torch.cuda.synchronize()
+
+
+def broadcast_factor(core, src=0, group=None, triangular=True, groups=8):
     """Replicate the factor state of ``core`` (a ``GPCore`` whose hypers and data are already set
-    on every rank) from rank ``src``: NCCL broadcast of L, L^-1 (n_pad^2 doubles each) and alpha
-    straight out of / into the handle's device buffers, then ``gpc_adopt_factor``."""
+    on every rank) from rank ``src``: NCCL broadcast of L, L^-1 (their lower block-triangles when ``triangular``,
+    0.5 + 0.5 / groups of the n_pad^2 doubles each) and alpha straight out of / into the handle's device buffers,
+    then ``gpc_adopt_factor``.  Returns {"bytes", "ms", "gbps"} (time between device synchronisations on this rank)."""
+    import time
     import torch
     import torch.distributed as dist
     pL, pX, pa, n_pad = core.factor_state_dev()
@@ -58,13 +104,51 @@ def broadcast_factor(core, src=0, group=None):
         meta[0] = core.logdet_
         meta[1] = 1.0
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
     dist.broadcast(meta, src, group=group)
-    for ptr, numel in ((pL, n_pad * n_pad), (pX, n_pad * n_pad), (pa, n_pad)):
-        t = _wrap_device_f64(ptr, numel)
-        dist.broadcast(t, src, group=group)
+    sent = 16
+    for ptr in (pL, pX):
+        t = _wrap_device_f64(ptr, n_pad * n_pad)
+        if triangular:
+            if rank != src:
+                t.zero_()                       # the upper triangle is never sent
+            sent += broadcast_lower(t.view(n_pad, n_pad), src, group, groups)
+        else:
+            dist.broadcast(t, src, group=group)
+            sent += n_pad * n_pad * 8
+    dist.broadcast(_wrap_device_f64(pa, n_pad), src, group=group)
+    sent += n_pad * 8
     torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
     if rank != src:
         core.adopt_factor(float(meta[0]))
+    return {"bytes": int(sent), "ms": 1e3 * dt, "gbps": sent / dt / 1e9}
+
+
+REDUNDANT_FACTOR_MAX_N = 4096
+
+
+def replicate_factor(core, src=0, group=None, redundant_max_n=REDUNDANT_FACTOR_MAX_N):
+    """Every rank ends up with the factor.  Up to ``redundant_max_n`` training points each rank factors its own copy
+    (2 ms at N = 2048, 5 ms at 4096: cheaper than moving 2 x 8 N^2 bytes and free of any collective -- SURVEY 8e);
+    beyond that rank ``src`` factors and the lower block-triangles are broadcast.
+    Returns {"mode", "factor_ms", "bytes", "ms", "gbps"}."""
+    import time
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if world == 1 or core.N <= redundant_max_n:
+        core.factor()
+        return {"mode": "redundant" if world > 1 else "single", "factor_ms": 1e3 * (time.perf_counter() - t0),
+                "bytes": 0, "ms": 0.0, "gbps": None}
+    if dist.get_rank(group) == src:
+        core.factor()
+    t_factor = time.perf_counter() - t0
+    st = broadcast_factor(core, src, group)
+    st.update(mode="broadcast_lower_triangles", factor_ms=1e3 * t_factor)
+    return st
 
 
 def _wrap_device_f64(ptr, numel):

@@ -42,6 +42,7 @@ METRIC = "GP posterior mean+var test pts/sec"
 MF2_PARAMS = np.array([4.0, 2.0, 3.0, 2.5, 1.0, 1.5, 2.0, 2.0, 0.8, 0.05, 0.02])   # var,l(3) x2, rho, noise x2
 MF3_PARAMS = np.array([3.0, 2.5, 3.5, 3.0, 1.0, 1.5, 2.0, 2.0, 0.5, 1.0, 1.5, 1.5, 0.9, 1.1, 0.08, 0.04, 0.02])
 DGEMM_PEAK_FILE = os.path.join(ROOT, "profiles", "microbench", "dgemm_peak_r01.json")
+I8_PEAK_FILE = os.path.join(ROOT, "profiles", "microbench", "umma_i8_peak_r02.json")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +331,20 @@ def run_ours(args):
     if nigp_mode:
         X4[:, 3] = 0.0
     n = int(round(M ** (1.0 / 3)))
-    if n ** 3 == M:
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE fixed test set of M_total points split contiguously over the ranks (configs[2]: 16 M points, N = 8192)
+        from gpcore.sharding import shard_range
+        M_total = M
+        lo_s, hi_s = shard_range(M_total, rank, world)
+        n = int(round(M_total ** (1.0 / 3)))
+        if n ** 3 == M_total and M_total <= (1 << 24):
+            Xs4_host = np.ascontiguousarray(make_grid(n, F - 1)[lo_s:hi_s])
+        else:
+            Xs4_host = np.hstack([np.random.default_rng(100).uniform([0, 0, 0], [10, 20, 10], (M_total, 3))[lo_s:hi_s],
+                                  np.full((hi_s - lo_s, 1), F - 1.0)])
+        M = hi_s - lo_s
+    elif n ** 3 == M:
         # every rank owns a different 1 M-point grid (shifted by a sub-cell offset) -> weak scaling
         Xs4_host = make_grid(n, F - 1, lo=0.01 * rank)
     else:
@@ -355,18 +369,10 @@ def run_ours(args):
         core.set_data(X4, y)
     mode = L.MODE_INT8 if args.mode == "int8" else L.MODE_FP64
     core.set_mode(mode)
-    t0 = time.perf_counter()
+    from gpcore.sharding import replicate_factor, warm_up
     if world > 1:
-        from gpcore.sharding import broadcast_factor
-        if rank == 0:
-            core.factor()
-        t_factor = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        broadcast_factor(core, 0)
-        t_bcast = time.perf_counter() - t0
-    else:
-        core.factor()
-        t_factor, t_bcast = time.perf_counter() - t0, 0.0
+        warm_up()            # communicator set-up (~1 s at 8 ranks) is not part of any factor broadcast
+    core.factor()            # first call: buffer allocation + first-touch; the timed replication below runs warm
 
     stream = torch.cuda.ExternalStream(core.stream())
     assert Xs4_host.flags["C_CONTIGUOUS"]
@@ -378,6 +384,27 @@ def run_ours(args):
 
     def step_dev():
         core.predict_dev(dXs.data_ptr(), M, dmean.data_ptr(), dvar.data_ptr(), flags)
+
+    # ---- the serial part: (re)factor -- redundantly on every rank up to N = 4096, else on rank 0 with the lower
+    # block-triangles of L and L^-1 NCCL-broadcast -- and the time to the FIRST result (factor + replication + one
+    # launch batch of this rank's points), max over ranks.  Warm buffers, outside the throughput region. ----------
+    m_first = min(M, args.chunk)
+    core.predict_dev(dXs.data_ptr(), m_first, dmean.data_ptr(), dvar.data_ptr(), flags)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    repl = replicate_factor(core, 0)
+    core.predict_dev(dXs.data_ptr(), m_first, dmean.data_ptr(), dvar.data_ptr(), flags)
+    torch.cuda.synchronize()
+    ttfr_ms = 1e3 * (time.perf_counter() - t0)
+    if dist is not None:
+        t = torch.tensor([ttfr_ms, repl["ms"], repl["factor_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ttfr_ms, repl["ms"], repl["factor_ms"] = float(t[0]), float(t[1]), float(t[2])
+        if repl["ms"] > 0:
+            repl["gbps"] = repl["bytes"] / (repl["ms"] * 1e-3) / 1e9
+    t_factor, t_bcast = 1e-3 * repl["factor_ms"], 1e-3 * repl["ms"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -417,7 +444,8 @@ def run_ours(args):
     hot_ms, hot_n, hot_flops = core.hot_kernel_time(reset=True)
     core.enable_hot_timing(False)
     clk = clocks.stop() if rank == 0 else None
-    value = world * M * args.steps / (ms * 1e-3)
+    pts_all_ranks = (M_total if strong else world * M)
+    value = pts_all_ranks * args.steps / (ms * 1e-3)
 
     # ---- e2e: reference-facing API, ORDINARY (pageable) NumPy arrays in and out, as a reference script passes them;
     # the library stages them through its own page-locked ring.  Copies inside the timed region.  The same call with
@@ -471,7 +499,7 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
-        return world * M * args.steps / dt
+        return pts_all_ranks * args.steps / dt
 
     e2e = time_e2e(Xs_plain)
     e2e_pinned = time_e2e(Xs_pinned)
@@ -502,6 +530,11 @@ def run_ours(args):
         noisy = {"value": M / dtn, "unit": "pts/s", "api": "gpcore.nigp.NIGP.predict(Xs, Xs_input_noise=sigma_x) (host buffers)",
                  "finite": bool(np.all(np.isfinite(var_n)) and np.all(np.isfinite(mu_n)))}
 
+    # ---- RIG information gain (the metric's second half): candidates sharded over ALL ranks, best node by NCCL -----
+    ig_line = None
+    if args.ig and not nigp_mode:
+        ig_line = bench_ig(args, gpcore, L, torch, dist, rank, world, local)
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -531,14 +564,18 @@ def run_ours(args):
     fp64_equiv = alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
     if args.mode == "int8":
         # 21 exact int8 digit GEMMs stand in for the FP64 contraction: report the kernel against the INT8 tensor peak
-        i8_peak = 4560.0   # TOP/s, tcgen05.mma kind::i8 N >= 128 measured on this B200 (profiles/r01/umma_i8_rate_r01.txt)
+        # the kernel is timed inside a long step that runs at the 1000 W power cap (profiles/r02/phase_power_r02.json):
+        # the roofline denominator is the SUSTAINED tcgen05 INT8 rate measured under the same cap; the burst rate
+        # (one isolated 2 ms launch) is listed next to it
+        i8_burst, i8_peak, i8_src = int8_peaks()
         achieved = 21.0 * alg_flops_per_launch / (avg_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "k_vt_i8<false,true> (V = L^-1 K* as 21 exact INT8 digit GEMMs, tcgen05 + TMEM, "
+        roofline = {"bound": "tensor", "kernel": "k_vt_i8<OUT_SUMSQ> (V = L^-1 K* as 21 exact INT8 digit GEMMs, tcgen05 + TMEM, "
                                                  "fused recombination and sum of squares)",
                     "achieved": achieved, "peak": i8_peak, "unit": "TOP/s (int8)", "frac": achieved / i8_peak, "traffic": traffic,
-                    "peak_source": "measured: tcgen05.mma.kind::i8 issue rate on this pool's B200 "
-                                   "(profiles/microbench/umma_i8_rate.cu, profiles/r01/umma_i8_rate_r01.txt); "
-                                   "MEASURED_PEAKS.json has no INT8 entry",
+                    "peak_burst": i8_burst, "frac_of_burst": achieved / i8_burst,
+                    "peak_source": i8_src + " (tcgen05.mma.kind::i8 M=128 N=256, random digit bytes; sustained = back-to-back "
+                                   "launches at the board's 1000 W power cap, which is where this step runs -- clocks.reasons "
+                                   "shows sw_power_cap; MEASURED_PEAKS.json has no INT8 entry)",
                     "launches": hot_n, "avg_launch_ms": avg_ms,
                     "algorithmic_ops_per_launch": 21.0 * alg_flops_per_launch,
                     "executed_ops_per_launch": 21.0 * hot_flops / max(hot_n, 1),
@@ -627,65 +664,147 @@ def run_ours(args):
                          % (M_cpu, M, N, cpu_factor, what)}
 
     line = {"metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(M * 16),
                     "api": api, "host_buffers": "pageable (plain numpy.ndarray) in and out", "pinned_input_value": e2e_pinned},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "mode": args.mode, "other_mode": other,
-            "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast, "factor": factor,
+            "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast, "factor_replication": repl,
+            "time_to_first_result_ms": ttfr_ms, "factor": factor,
             "mean_only": mean_only, "noisy_input": noisy, "parity": parity}
 
-    if args.ig and not nigp_mode:
-        line["ig"] = bench_ig(args, gpcore, L, torch, local)
+    line["ig"] = ig_line
     emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def bench_ig(args, gpcore, L, torch, local):
-    """Secondary metric: RIG log-det information-gain evaluations per second (configs[3])."""
-    N, F, C, k = 4096, 3, args.ig_candidates, 32
+def int8_peaks():
+    """tcgen05 INT8 peaks measured on this pool's B200 by profiles/microbench/umma_i8_sustained.cu (random digit bytes):
+    burst (one 2 ms launch) and sustained (back-to-back launches, the 1000 W power cap sets the clock)."""
+    try:
+        pk = json.load(open(I8_PEAK_FILE))
+        return float(pk["burst_tops"]), float(pk["sustained_tops"]), "measured: profiles/microbench/umma_i8_peak_r02.json"
+    except Exception:
+        return 4341.7, 3774.4, "fallback: the figures profiles/microbench/umma_i8_sustained.cu measured in round 2"
+
+
+def cpu_ig_baseline(N, F, k, grid4, X4, y, rows, offs, n_literal=3, n_schur=256):
+    """The reference's way (calculatePathInfoEmuBatch, PhysicalExperimentCode/GraceRIGV3.py:599-618: one full refit of
+    the (N + k)-point model and two G x G determinants per candidate) on a bounded sample, and the Schur-complement
+    port of the same quantity, both on the host cores."""
+    from oracle import gp_oracle as go
+    t0 = time.perf_counter()
+    ref = go.MFGP(X4, y, MF3_PARAMS, F=F)
+    t_fit = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lit = [go.ig_logdet_refit(ref, grid4, rows[offs[c]:offs[c + 1]], clip_cov=1e-10) for c in range(n_literal)]
+    t_lit = time.perf_counter() - t0
+    _, _, _, noise = go.split_mf_params(MF3_PARAMS, F)
+    t0 = time.perf_counter()
+    sch = [go.ig_logdet_schur(ref, grid4, rows[offs[c]:offs[c + 1]], noise[2], noise[rows[offs[c]:offs[c + 1], 3].astype(int)])
+           for c in range(n_schur)]
+    t_sch = time.perf_counter() - t0
+    return {"value": n_literal / t_lit, "unit": "evals/s", "cores": blas_threads(), "kind": "port",
+            "sample": "%d of the candidates by the literal refit loop (one O((N + k)^3) refit + two 300 x 300 determinants "
+                      "per candidate, as the reference does; model fit %.1f s outside the sample), N=%d, k=%d"
+                      % (n_literal, t_fit, N, k),
+            "schur_port_value": n_schur / t_sch, "schur_port_sample": "%d candidates by the k x k determinant-lemma form" % n_schur,
+            "finite": bool(np.all(np.isfinite(lit)) and np.all(np.isfinite(sch)))}
+
+
+def bench_ig(args, gpcore, L, torch, dist, rank, world, local):
+    """RIG info-gain evaluations per second (BASELINE metric, second half; configs[3]): N = 4096 three-fidelity MF-GP,
+    65536 candidate nodes x 32 points, G = 300 grid.  The factor is replicated (every rank factors: N <= 4096), the
+    candidates are sharded contiguously over the ranks, every rank scores its share, and one 16-byte all-gather picks the
+    best node (gpcore.sharding.reduce_best) -- inside the timed region, because it is part of the path it replaces
+    (the serial scan GraceRIGV3.py:1072-1189).  Host buffers in, scores + argmax out (the C ABI call a planner makes)."""
+    from gpcore.sharding import reduce_best, shard_candidates
+    N, F, C, k, G = 4096, 3, args.ig_candidates, 32, 300
     X4, y = make_train(N, F, seed=3)
     core = gpcore.GPCore(L.KIND_MF_AR1_RBF, F, local)
     core.set_hypers(MF3_PARAMS, 1e-8)
     core.set_data(X4, y)
     core.factor()
     g = np.meshgrid(np.linspace(0, 10, 10), np.linspace(0, 20, 6), np.linspace(0, 10, 5))
-    grid4 = np.ascontiguousarray(np.hstack([np.array([gi.ravel("F") for gi in g]).T, 2 * np.ones((300, 1))]))
-    rows, offs = make_candidates(C, k, F)
-    # warm-up: one untimed call of each operator at full size (buffers of the candidate set, first-touch), as a
-    # planner that rescans its tree every plan() sees it
-    core.ig_logdet(grid4, rows, offs)
-    core.ig_seq(rows, offs, MF3_PARAMS[-1], pred_fid=0)
-    torch.cuda.synchronize()
+    grid4 = np.ascontiguousarray(np.hstack([np.array([gi.ravel("F") for gi in g]).T, 2 * np.ones((G, 1))]))
+    rows, offs = make_candidates(C, k, F)                 # the same seeded set on every rank
+    c_lo, c_hi, loffs, r_lo, r_hi = shard_candidates(offs, rank, world)
+    lrows = np.ascontiguousarray(rows[r_lo:r_hi])
+    sig_n = float(MF3_PARAMS[-1])
+    ops = {"logdet": lambda: core.ig_logdet(grid4, lrows, loffs)[::2],
+           "seq": lambda: core.ig_seq(lrows, loffs, sig_n, pred_fid=0),
+           "logdet_clip": lambda: core.ig_logdet(grid4, lrows, loffs, clip=True)[::2]}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    res, scores = {}, {}
     core.enable_hot_timing(True)
-    core.hot_kernel_time(reset=True)
-    t0 = time.perf_counter()
-    I, prior, best = core.ig_logdet(grid4, rows, offs)
-    dt_ld = time.perf_counter() - t0
-    hot_ms, hot_n, hot_fl = core.hot_kernel_time(reset=True)
-    t0 = time.perf_counter()
-    Is, bests = core.ig_seq(rows, offs, MF3_PARAMS[-1], pred_fid=0)
-    dt_seq = time.perf_counter() - t0
-    hot_ms2, hot_n2, hot_fl2 = core.hot_kernel_time(reset=True)
-    # calculatePathInfoEmuBatch as the reference computes it (emukit's element-wise 1e-10 clip of both G x G
-    # covariances: one 300 x 300 factorisation per candidate instead of a k x k update), on a bounded subset
-    Cc = min(C, 8192)
-    core.ig_logdet(grid4, rows[:k * Cc], offs[:Cc + 1], clip=True)
-    t0 = time.perf_counter()
-    Ic, _, _ = core.ig_logdet(grid4, rows[:k * Cc], offs[:Cc + 1], clip=True)
-    dt_clip = time.perf_counter() - t0
+    for name, fn in ops.items():
+        fn()                                              # warm-up at full size (buffers, first touch)
+        barrier()
+        core.hot_kernel_time(reset=True)
+        t0 = time.perf_counter()
+        I, lbest = fn()
+        bv, bi = (float(I[lbest]), int(lbest) + c_lo) if dist is None else \
+            reduce_best(I[lbest] if lbest >= 0 else 0.0, lbest, c_lo)
+        dt = time.perf_counter() - t0
+        dev_ms = core.last_call_device_ms()
+        hot_ms, hot_n, hot_fl = core.hot_kernel_time(reset=True)
+        if dist is not None:
+            t = torch.tensor([dt, dev_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, dev_ms = float(t[0]), float(t[1])
+        res[name] = dict(dt=dt, dev_ms=dev_ms, hot_ms=hot_ms, hot_n=hot_n, hot_fl=hot_fl, best=bi, best_value=bv,
+                         finite=bool(np.all(np.isfinite(I))))
+        scores[name] = I
+    core.enable_hot_timing(False)
+    # the sharded winner must be the single-rank argmax over ALL candidates (rank 0 scores the full set, untimed)
+    verified = None
+    if rank == 0:
+        if world > 1:
+            If, _, bf = core.ig_logdet(grid4, rows, offs)
+            Isf, bsf = core.ig_seq(rows, offs, sig_n, pred_fid=0)
+            verified = bool(res["logdet"]["best"] == int(bf) and res["logdet"]["best_value"] == float(If[bf])
+                            and res["seq"]["best"] == int(bsf) and res["seq"]["best_value"] == float(Isf[bsf]))
+        else:
+            verified = bool(res["logdet"]["best"] == int(np.argmax(scores["logdet"])))
     core.close()
-    return {"metric": "RIG info-gain evals/sec (host buffers in, scores + argmax out)", "n_train": N, "fidelities": F,
-            "candidates": C, "points_per_candidate": k, "grid": 300,
-            "logdet_evals_per_s": C / dt_ld, "seq_evals_per_s": C / dt_seq,
-            "logdet_clip_evals_per_s": Cc / dt_clip, "logdet_clip_candidates": Cc,
-            "logdet_clip_finite": bool(np.all(np.isfinite(Ic))),
-            "logdet_alg_tflops": C * (k * N * N + 2.0 * k * 300 * N + k * k * N) / dt_ld / 1e12,
-            "hot_kernel_tflops_executed": (hot_fl + hot_fl2) / ((hot_ms + hot_ms2) * 1e-3) / 1e12,
-            "finite": bool(np.all(np.isfinite(I)) and np.all(np.isfinite(Is))), "best": int(best)}
+    if rank != 0:
+        return None
+    burst, sustained, src = int8_peaks()
+    ld = res["logdet"]
+    # SURVEY 8d, per candidate: k N^2 (V = L^-1 K*) + 2 k G N (cross term with the grid's V) + k^2 N (Gram); each FP64
+    # multiply-add pair is 21 exact INT8 digit products on the tensor cores
+    alg = float(c_hi - c_lo) * (k * float(N) * N + 2.0 * k * G * N + float(k) * k * N)
+    ach = 21.0 * alg / (ld["hot_ms"] * 1e-3) / 1e12
+    line = {"metric": "RIG info-gain evals/sec", "unit": "evals/s", "n_gpus": world, "scaling": "strong",
+            "value": C / (ld["dev_ms"] * 1e-3), "operator": "log-det IG on the fixed grid (gpc_ig_logdet: calcPathInfoSFBatch / "
+            "calculatePathInfoEmuBatch without emukit's clip), device time by CUDA events (staged uploads included), max over ranks",
+            "e2e": {"value": C / ld["dt"], "unit": "evals/s", "h2d_bytes_per_step": int(lrows.nbytes + loffs.nbytes + grid4.nbytes),
+                    "d2h_bytes_per_step": int(8 * (c_hi - c_lo) + 8),
+                    "api": "GPCore.ig_logdet -> gpc_ig_logdet_ex (pageable host arrays in, scores + argmax out) + reduce_best"},
+            "config": {"workload": "configs[3]: RIG info-gain scoring of %d candidate tree nodes x %d points against an N=%d "
+                                   "three-fidelity MF-GP, %d-point grid, candidates sharded over %d GPU(s)" % (C, k, N, G, world),
+                       "n_train": N, "fidelities": F, "candidates": C, "points_per_candidate": k, "grid": G},
+            "operators": {nm: {"value": C / (r["dev_ms"] * 1e-3), "e2e": C / r["dt"], "best": r["best"], "finite": r["finite"]}
+                          for nm, r in res.items()},
+            "sharded_best_equals_single_rank_argmax": verified,
+            "roofline": {"bound": "tensor", "kernel": "k_vt_i8<OUT_DIGITS> + k_vt_i8<OUT_F64, FULLK> (V = L^-1 K* emitted as a digit "
+                         "image, diagonal-tile Gram blocks and cross products with the grid's V from it), rank 0's launches",
+                         "achieved": ach, "peak": sustained, "unit": "TOP/s (int8)", "frac": ach / sustained,
+                         "peak_burst": burst, "frac_of_burst": ach / burst, "peak_source": src + " (sustained: the kernels run "
+                         "inside a long power-capped step)", "launches": ld["hot_n"], "avg_launch_ms": ld["hot_ms"] / max(ld["hot_n"], 1),
+                         "algorithmic_ops": 21.0 * alg, "executed_ops": 21.0 * ld["hot_fl"], "share_of_call": ld["hot_ms"] / ld["dev_ms"],
+                         "traffic": None},
+            "cpu_baseline": cpu_ig_baseline(N, F, k, grid4, X4, y, rows, offs) if world == 1 else None}
+    return line
 
 
 _STDOUT_FD = None
@@ -723,6 +842,8 @@ def main():
     ap.add_argument("--n-train", type=int, default=0)
     ap.add_argument("--m-test", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --m-test points PER GPU (default); strong: ONE set of --m-test points split over the GPUs")
     ap.add_argument("--parity", type=int, default=1, help="check the timed results against the CPU oracle (4096 points)")
     ap.add_argument("--ig", type=int, default=1)
     ap.add_argument("--ig-candidates", type=int, default=65536)

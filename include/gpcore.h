@@ -214,6 +214,9 @@ int gpc_get_mode(gpc_handle h);
  * on gpc_stream() since the last reset, the number of its launches and the floating-point
  * operations those launches executed (2 x multiply-adds over the padded triangular k-range). */
 int gpc_hot_kernel_time(gpc_handle h, double* ms_total, long* launches, double* flops, int reset);
+/* Device time (CUDA events on gpc_stream(), first to last kernel, the staged uploads of the candidate rows
+ * included) of the most recent information-gain call on this handle: the rate with the inputs already in HBM. */
+int gpc_last_call_device_ms(gpc_handle h, double* ms);
 int gpc_enable_hot_timing(gpc_handle h, int on);
 
 #ifdef __cplusplus

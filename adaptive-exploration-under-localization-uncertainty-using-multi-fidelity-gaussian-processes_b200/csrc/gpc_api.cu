@@ -75,8 +75,19 @@ std::string g_create_error;
 
 }  // namespace
 
+// One captured factorisation (Cholesky + triangular inverse of a given buffer set): ~100 launches on three streams
+// replayed as a single CUDA graph, which removes the per-launch host cost and most of the gap between dependent kernels.
+struct FactorGraph {
+  double *A = nullptr, *X = nullptr, *T = nullptr;
+  long n_pad = 0;
+  int* status = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long launches = 0;
+};
+
 struct gpc_handle_s {
   int kind = 0, F = 1, device = 0;
+  std::vector<FactorGraph> graphs;
   cudaStream_t stream = nullptr, side = nullptr;   // side: look-ahead stream of the factorisation
   cudaStream_t inv = nullptr;                      // early part of the triangular inverse (runs under the Cholesky tail)
   cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_half = nullptr, ev_inv = nullptr;
@@ -177,11 +188,15 @@ int set_gemm_attrs(gpc_handle h) {
 // the main stream; the serial chain of that pair -- diagonal block (one CTA), panel solve, rank-128
 // update of the pair's second block column, second diagonal block, second panel solve -- then runs
 // on the side stream while the main stream finishes the rank-256 update of the rest.
-int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int* d_status) {
+int factor_matrix_launch(gpc_handle h, double* A, double* X, double* T, long n_pad, int* d_status) {
   const int nb = (int)(n_pad / 128);
   cudaStream_t s = h->stream, s2 = h->side;
   const int half = nb / 2;
-  const bool early = nb >= 8 && (nb & (nb - 1)) == 0;   // power-of-two block count: the recursion splits at nb / 2
+  // profiling only (bench.py factor_8192): GPC_FACTOR_PHASE=chol stops after the Cholesky (L^-1 is then NOT formed and
+  // nothing downstream is valid) so that the Cholesky alone can be timed
+  const char* phase_env = std::getenv("GPC_FACTOR_PHASE");
+  const bool chol_only = phase_env && std::strcmp(phase_env, "chol") == 0;
+  const bool early = !chol_only && nb >= 8 && (nb & (nb - 1)) == 0;   // power-of-two block count: the recursion splits at nb / 2
   CK(cudaMemsetAsync(d_status, 0, sizeof(int), s));
   k_potrf_diag<<<1, GPC_PD_NT, GPC_POTRF_SMEM, s>>>(A, X, n_pad, 0, d_status);
   CKL();
@@ -255,6 +270,7 @@ int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int
     CKL();
     return GPC_OK;
   }
+  if (chol_only) return GPC_OK;
   for (int sb = 1; sb < nb; sb *= 2) {
     const int nodes = (nb + 2 * sb - 1) / (2 * sb);
     for (int phase = 0; phase < 2; ++phase) {
@@ -265,11 +281,53 @@ int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int
   return GPC_OK;
 }
 
+// The factorisation as a CUDA graph: captured the first time a buffer set is factored (thread-local capture of the
+// three streams of factor_matrix_launch), replayed afterwards.  At N = 2048 the chain is launch-latency bound (16
+// serial panels x 4 dependent kernels); beyond GPC_GRAPH_MAX_N the kernels are long enough for plain launches.
+#define GPC_GRAPH_MAX_N 4096
+int factor_matrix(gpc_handle h, double* A, double* X, double* T, long n_pad, int* d_status) {
+  static const bool no_graph = std::getenv("GPC_NO_GRAPH") != nullptr;
+  if (n_pad > GPC_GRAPH_MAX_N || no_graph || std::getenv("GPC_FACTOR_PHASE")) return factor_matrix_launch(h, A, X, T, n_pad, d_status);
+  for (const FactorGraph& g : h->graphs)
+    if (g.A == A && g.X == X && g.T == T && g.n_pad == n_pad && g.status == d_status) {
+      CK(cudaGraphLaunch(g.exec, h->stream));
+      h->launches += g.launches;
+      return GPC_OK;
+    }
+  const long l0 = h->launches;
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    const int rc = factor_matrix_launch(h, A, X, T, n_pad, d_status);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == GPC_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == GPC_OK && e == cudaSuccess && exec) {
+      FactorGraph g;
+      g.A = A; g.X = X; g.T = T; g.n_pad = n_pad; g.status = d_status; g.exec = exec; g.launches = h->launches - l0;
+      if (h->graphs.size() >= 8) {            // buffers were re-allocated a few times: drop the oldest capture
+        cudaGraphExecDestroy(h->graphs.front().exec);
+        h->graphs.erase(h->graphs.begin());
+      }
+      h->graphs.push_back(g);
+      h->launches = l0;
+      CK(cudaGraphLaunch(exec, h->stream));
+      h->launches += g.launches;
+      return GPC_OK;
+    }
+    cudaGetLastError();                       // capture or instantiation failed: plain launches
+    h->launches = l0;
+  } else {
+    cudaGetLastError();
+  }
+  return factor_matrix_launch(h, A, X, T, n_pad, d_status);
+}
+
 // out = M^T x (+ bias) via two-stage partial sums.
 int trmv_t(gpc_handle h, const double* M, const double* x, const double* bias, double bias_scale, double sign,
            double* out) {
   const int nb = h->nb;
-  k_trmv_t_partial<<<dim3(nb, nb), 128, 0, h->stream>>>(M, h->n_pad, x, h->partial.d(), h->n_pad);
+  k_trmv_t_partial<<<dim3(nb, nb), 512, 0, h->stream>>>(M, h->n_pad, x, h->partial.d(), h->n_pad);
   CKL();
   k_colsum_partial<<<(unsigned)((h->n_pad + 255) / 256), 256, 0, h->stream>>>(h->partial.d(), nb, h->n_pad, bias,
                                                                             bias_scale, sign, out);
@@ -679,6 +737,8 @@ int gpc_destroy(gpc_handle h) {
                     &h->cand_off, &h->cand_I, &h->cand_aux, &h->cand_rows, &h->cand_mask, &h->gram, &h->gramZ};
   for (DevBuf* b : bufs) b->release();
   h->pin_in.release(); h->pin_sx.release(); h->pin_mean.release(); h->pin_var.release();
+  for (FactorGraph& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
@@ -827,20 +887,21 @@ int gpc_factor(gpc_handle h, double* nlml, double* logdet) {
   CKL();
   int rc = factor_matrix(h, h->L.d(), h->X.d(), h->T.d(), np, static_cast<int*>(h->status.p));
   if (rc) return rc;
+  // alpha and the log-det are queued behind the factorisation without waiting for its status (a non-PD matrix only
+  // makes them garbage, which is never returned): ONE host synchronisation per gpc_factor
+  if ((rc = solve_alpha(h))) return rc;
+  k_logdet_fit<<<1, 1024, 0, h->stream>>>(h->L.d(), np, h->N, h->y.d(), h->alpha.d(), h->scal.d());
+  CKL();
   int st = 0;
+  double sc[2];
   CK(cudaMemcpyAsync(&st, h->status.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (st != 0) {
     char buf[128];
     snprintf(buf, sizeof buf, "covariance not positive definite (pivot block %d)", st - 1);
     return fail(h, GPC_ERR_NOT_PD, buf);
   }
-  if ((rc = solve_alpha(h))) return rc;
-  k_logdet_fit<<<1, 1024, 0, h->stream>>>(h->L.d(), np, h->N, h->y.d(), h->alpha.d(), h->scal.d());
-  CKL();
-  double sc[2];
-  CK(cudaMemcpyAsync(sc, h->scal.p, 16, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   if (!std::isfinite(sc[0]) || !std::isfinite(sc[1]))
     return fail(h, GPC_ERR_NOT_PD, "non-finite factor (covariance not positive definite)");
   h->logdet = sc[0];

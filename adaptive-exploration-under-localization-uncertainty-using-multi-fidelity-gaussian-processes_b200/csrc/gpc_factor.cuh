@@ -40,22 +40,26 @@ __global__ void __launch_bounds__(256) k_assemble_train(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// Diagonal block p: L_pp = chol(A_pp) and X_pp = L_pp^-1, one CTA of 256 threads working out of
+// Diagonal block p: L_pp = chol(A_pp) and X_pp = L_pp^-1, one CTA of 512 threads working out of
 // shared memory.  It sits on the critical path of the factorisation (nb serial launches), so it
-// is organised for latency: 8 steps over 16-column sub-blocks, three barriers each,
-//   (1) warp 0 factors the 16 x 16 diagonal sub-block in registers (one row per lane, pivots and
-//       multipliers exchanged by warp shuffles, rsqrt instead of sqrt + divide) and inverts it by
-//       a right-looking substitution (15 independent updates per step);
-//   (2) threads 0..111 solve the rows below against that inverse (L panel) while threads
-//       128..239 finish block row kb of the inverse, X_kb,: = T_kb Y_kb,:;
-//   (3) all threads apply rank-16 updates in 4 x 4 register micro-tiles: to the trailing
-//       sub-matrix (Cholesky) and to the running right-hand side Y of L X = I (inverse).
-// X^T (and Y before it) lives in the unused upper triangle of the same shared array: leading
-// dimension 129 leaves room for the shifted diagonal.
+// is organised for latency: 8 steps over 16-column sub-blocks, two barriers each,
+//   (1) warp 0 factors AND inverts the 16 x 16 diagonal sub-block in one register-resident pass (one row of L and
+//       one column of L^-1 per lane, pivots and multipliers exchanged by warp shuffles, rsqrt instead of sqrt +
+//       divide) -- for step kb + 1 this runs UNDER phase (3) of step kb;
+//   (2) panel products on the FP64 tensor cores (DMMA 8x8x4, 8 x 8 output tiles, K = 16):
+//       L[r0:, c0:c0+16] = A[r0:, c0:c0+16] T^T  (one warp per 8-row tile) and block row kb of the inverse,
+//       X[c0:c0+16, :c0] = T Y[c0:c0+16, :c0]  (one warp per 8-column tile);
+//   (3) rank-16 updates as DMMA tiles: the trailing sub-matrix A[r0:, r0:] -= P P^T (lower tiles) and the
+//       running right-hand side of L X = I,  Y[r0:, :r0] -= P X[c0:c0+16, :r0].
+// X^T (and Y before it) lives in the unused upper triangle of the same shared array, shifted by one column;
+// the leading dimension 132 makes every DMMA fragment load (one double per lane) bank-conflict free.
 // status receives p + 1 for the first non-positive pivot.
 // replaces: scipy cho_factor (NIGP.py:43,154,288) / LAPACK dpotrf inside GPy pdinv.
 // ------------------------------------------------------------------------------------------
-#define GPC_PD_LD 129
+#define GPC_PD_LD 132
+#ifndef GPC_PD_SKIP
+#define GPC_PD_SKIP 0   // profiling only (profiles/microbench/potrf_diag_phases.cu): 1 tiles off, 2 serial 16 x 16 off, 4 global I/O off
+#endif
 constexpr int GPC_POTRF_SMEM = (128 * GPC_PD_LD + 32) * 8;
 
 constexpr int GPC_PD_NT = 512;   // threads of the diagonal-block CTA
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(GPC_PD_NT, 1) k_potrf_diag(double* __restrict_
   double* S = sm;  // L in the lower triangle (incl. diagonal), X^T above it
 #define XT(i, j) S[(j) * GPC_PD_LD + (i) + 1]  // X(i, j), i >= j
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
   double* Ap = A + (long)p * 128 * ld + (long)p * 128;
   double* Xp = X + (long)p * 128 * ld + (long)p * 128;
   __shared__ int bad;
@@ -72,184 +77,168 @@ __global__ void __launch_bounds__(GPC_PD_NT, 1) k_potrf_diag(double* __restrict_
 #pragma unroll 8
   for (int e = tid; e < 128 * 128; e += GPC_PD_NT) {
     const int r = e >> 7, c = e & 127;
-    const double v = (c <= r) ? Ap[(long)r * ld + c] : 0.0;
+    const double v = (c <= r) ? ((GPC_PD_SKIP & 4) ? (r == c ? 1.0 : 0.0) : Ap[(long)r * ld + c]) : 0.0;
     if (c <= r) S[r * GPC_PD_LD + c] = v;
     else S[r * GPC_PD_LD + c + 1] = 0.0;  // Y = 0 (slot of X(c, r))
   }
   __syncthreads();
 
-  // Software pipeline over the eight 16-column steps: while warps 1..15 apply the rank-16 update of step kb,
-  // warp 0 updates just the NEXT 16 x 16 diagonal sub-block and factors / inverts it (the serial part of step
-  // kb + 1), so that it is off the critical path of every step but the first.
   auto factor16 = [&](int c0) {
-    // (1) 16 x 16 diagonal sub-block: lane l owns row l in registers; the pivot's reciprocal
-    //     square root and the column of multipliers travel through shared memory (broadcast
-    //     reads), two __syncwarp per column -- no shuffle chains on the critical path.
-    const int l = lane & 15;  // lanes 16..31 shadow lanes 0..15
-    double* colb = S + 128 * GPC_PD_LD;  // 16 multipliers
-    double* invs = colb + 16;          // 16 reciprocal pivots
-    double a[16];
+    if (GPC_PD_SKIP & 2) return;
+    // 16 x 16 diagonal sub-block L_kk and T = L_kk^-1 in ONE pass, entirely in registers: lane l owns row l of L and
+    // column l of T (lanes 16..31 mirror lanes 0..15).  Per column k: the pivot travels by one shuffle, every lane
+    // takes its reciprocal square root itself (no second broadcast), and the multipliers L[j][k], j > k -- one shuffle
+    // each -- feed both the rank-1 update of the trailing rows and the right-looking substitution for T.  The chain
+    // shuffle -> rsqrt -> scale -> shuffle -> fma per column is the critical path of the whole diagonal block.
+    const int l = lane & 15;
+    double a[16], x[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = (j <= l) ? S[(c0 + l) * GPC_PD_LD + c0 + j] : 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (lane == k) {
-        double d = a[k];
-        if (!(d > 0.0)) { bad = 1; d = 1.0; }
-        double inv = rsqrt(d);
-        inv = inv * fma(-0.5 * d * inv, inv, 1.5);  // one more Newton step: full double accuracy
-        invs[k] = inv;
-      }
-      __syncwarp();
-      const double inv = invs[k];
-      if (l == k) a[k] *= inv;  // d / sqrt(d) = sqrt(d)
-      else if (l > k) {
-        a[k] *= inv;
-        if (lane < 16) colb[l] = a[k];
-      }
-      __syncwarp();
+    for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
 #pragma unroll
-      for (int j = k + 1; j < 16; ++j)
-        if (l >= j) a[j] = fma(-a[k], colb[j], a[j]);
+    for (int k = 0; k < 16; ++k) {
+      double d = __shfl_sync(0xffffffffu, a[k], k);
+      if (!(d > 0.0)) {
+        if (lane == 0) bad = 1;
+        d = 1.0;
+      }
+      const double inv = rsqrt(d);
+      a[k] *= inv;                       // L[l][k]; on the diagonal d / sqrt(d) = sqrt(d)
+      x[k] *= inv;                       // T[k][l]
+#pragma unroll
+      for (int j = k + 1; j < 16; ++j) {
+        const double cj = __shfl_sync(0xffffffffu, a[k], j);   // L[j][k]
+        a[j] = fma(-a[k], cj, a[j]);     // entries right of the diagonal (j > l) are never read back
+        x[j] = fma(-cj, x[k], x[j]);
+      }
     }
     if (lane < 16) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j <= l) S[(c0 + l) * GPC_PD_LD + c0 + j] = a[j];
-    }
-    __syncwarp();
-    // T = L_kk^-1, column l per lane, right-looking; L is read back from shared memory (broadcast)
-    double x[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = (i == l) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      x[k] *= invs[k];
-#pragma unroll
-      for (int i = k + 1; i < 16; ++i) x[i] = fma(-S[(c0 + i) * GPC_PD_LD + c0 + k], x[k], x[i]);
-    }
-    if (lane < 16) {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         if (i >= l) XT(c0 + i, c0 + l) = x[i];
     }
   };
-  auto chol_tile = [&](int r0, int c0, int ti, int tj) {
-    double c[4][4];
+  // (3a) trailing tile (I, J), J <= I, of A[r0:, r0:] -= P P^T with P = L[r0:, c0:c0+16]; only j <= i is stored (the
+  // slots right of the diagonal belong to X^T).  (Groups of four tiles per warp with shared A fragments were tried:
+  // no faster -- the phase runs at about half the DMMA rate of one SM and is balance-, not latency-bound;
+  // profiles/r02/README.md.)
+  auto chol_tile = [&](int r0, int c0, int I, int J) {
+    const int ri = r0 + 8 * I + lr, rj = r0 + 8 * J + lr, cj = r0 + 8 * J + 2 * lc;
+    double acc0 = S[ri * GPC_PD_LD + cj], acc1 = S[ri * GPC_PD_LD + cj + 1];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
-    const double* Pi = S + (r0 + 4 * ti) * GPC_PD_LD + c0;
-    const double* Pj = S + (r0 + 4 * tj) * GPC_PD_LD + c0;
-#pragma unroll 4
-    for (int m = 0; m < 16; ++m) {
-      double ai[4], aj[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { ai[u] = Pi[u * GPC_PD_LD + m]; aj[u] = Pj[u * GPC_PD_LD + m]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], aj[v], c[u][v]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const int i = r0 + 4 * ti + u, j = r0 + 4 * tj + v;
-        if (j <= i) S[i * GPC_PD_LD + j] -= c[u][v];
-      }
+    for (int s4 = 0; s4 < 4; ++s4)
+      dmma884(acc0, acc1, -S[ri * GPC_PD_LD + c0 + 4 * s4 + lc], S[rj * GPC_PD_LD + c0 + 4 * s4 + lc]);
+    if (cj <= ri) S[ri * GPC_PD_LD + cj] = acc0;
+    if (cj + 1 <= ri) S[ri * GPC_PD_LD + cj + 1] = acc1;
   };
+  // (3b) tile (I, J) of Y[r0:, :r0] -= P X[c0:c0+16, :r0]  (X block row kb is final: zero right of its diagonal)
+  auto inv_tile = [&](int r0, int c0, int I, int J) {
+    const int r = r0 + 8 * I + lr, cC = 8 * J + 2 * lc, cB = 8 * J + lr;
+    double acc0 = XT(r, cC), acc1 = XT(r, cC + 1);
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int m = c0 + 4 * s4 + lc;
+      const double b = (cB <= m) ? XT(m, cB) : 0.0;
+      dmma884(acc0, acc1, -S[r * GPC_PD_LD + m], b);
+    }
+    XT(r, cC) = acc0;
+    XT(r, cC + 1) = acc1;
+  };
+
   if (warp == 0) factor16(0);
   __syncthreads();
 #pragma unroll 1
   for (int kb = 0; kb < 8; ++kb) {
     const int c0 = kb * 16;
     const int r0 = c0 + 16, nrow = 128 - r0;
-    if (tid < nrow) {
-      // (2a) panel: L[r][c0 + c] = sum_{m <= c} A[r][c0 + m] T[c][m]
-      const int r = r0 + tid;
-      double av[16], out[16];
+    const int mt = nrow >> 3;          // 8-row tiles below the sub-block
+    // ---- (2) panel products with T = L_kk^-1 (X^T slots of the sub-block) ----------------------------------
+    const int n2a = mt, n2b = c0 >> 3;
+    for (int t = warp; t < ((GPC_PD_SKIP & 1) ? 0 : n2a + n2b); t += GPC_PD_NT / 32) {
+      if (t < n2a) {
+        // L[r][c0 + c] = sum_{m <= c} A[r][c0 + m] T[c][m]: the warp owns rows r0 + 8 t .. + 7 and both 8-column tiles
+        const int r = r0 + 8 * t + lr;
+        double a[4], o[2][2];
 #pragma unroll
-      for (int m = 0; m < 16; ++m) av[m] = S[r * GPC_PD_LD + c0 + m];
+        for (int s4 = 0; s4 < 4; ++s4) a[s4] = S[r * GPC_PD_LD + c0 + 4 * s4 + lc];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        double sacc = 0.0;
+        for (int nt = 0; nt < 2; ++nt) {
+          o[nt][0] = o[nt][1] = 0.0;
+          const int cc = 8 * nt + lr;
 #pragma unroll
-        for (int m = 0; m <= c; ++m) sacc = fma(av[m], XT(c0 + c, c0 + m), sacc);
-        out[c] = sacc;
-      }
-#pragma unroll
-      for (int c = 0; c < 16; ++c) S[r * GPC_PD_LD + c0 + c] = out[c];
-    } else if (tid >= 128 && tid - 128 < c0) {
-      // (2b) inverse, block row kb: X[c0 + i][j] = sum_{t <= i} T[i][t] Y[c0 + t][j],  j < c0
-      const int j = tid - 128;
-      double yv[16], out[16];
-#pragma unroll
-      for (int t = 0; t < 16; ++t) yv[t] = XT(c0 + t, j);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int t = 0; t <= i; ++t) sacc = fma(XT(c0 + i, c0 + t), yv[t], sacc);
-        out[i] = sacc;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) XT(c0 + i, j) = out[i];
-    }
-    __syncthreads();
-    // (3) rank-16 updates in 4 x 4 micro-tiles: the trailing Cholesky tiles (lower triangle of nt x nt) and the
-    //     inverse's right-hand side Y[r][c] -= L[r][c0:c0+16] X[c0:c0+16][c], c < r0.  Warp 0 takes the ten tiles of
-    //     the next diagonal sub-block and goes on to factor it; the other warps share everything else.
-    const int nt = nrow >> 2, nchol = nt * nt, ncx = r0 >> 2, ntot = nchol + nt * ncx;
-    if (warp == 0) {
-      if (nt > 0) {
-        if (lane < 10) {
-          const int ti = lane < 1 ? 0 : (lane < 3 ? 1 : (lane < 6 ? 2 : 3));
-          const int tj = lane - (ti * (ti + 1)) / 2;
-          chol_tile(r0, c0, ti, tj);
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int m = 4 * s4 + lc;
+            const double b = (m <= cc) ? XT(c0 + cc, c0 + m) : 0.0;
+            dmma884(o[nt][0], o[nt][1], a[s4], b);
+          }
         }
         __syncwarp();
-        factor16(r0);
-      }
-    } else {
-      for (int idx = tid - 32; idx < ntot; idx += GPC_PD_NT - 32) {
-        if (idx < nchol) {
-          const int ti = idx / nt, tj = idx - ti * nt;
-          if (tj > ti || ti < 4) continue;          // upper triangle / warp 0's tiles
-          chol_tile(r0, c0, ti, tj);
-        } else {
-          double c[4][4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+        for (int nt = 0; nt < 2; ++nt) {
+          S[r * GPC_PD_LD + c0 + 8 * nt + 2 * lc] = o[nt][0];
+          S[r * GPC_PD_LD + c0 + 8 * nt + 2 * lc + 1] = o[nt][1];
+        }
+      } else {
+        // X[c0 + i][j] = sum_{t <= i} T[i][t] Y[c0 + t][j], j < c0: the warp owns columns 8 J .. + 7 and both 8-row tiles
+        const int J = t - n2a;
+        double b[4], o[2][2];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) c[u][v] = 0.0;
-          const int e = idx - nchol;
-          const int ti = e / ncx, tc = e - ti * ncx;
-          const int rr = r0 + 4 * ti, cc = 4 * tc;
-          const double* Pi = S + rr * GPC_PD_LD + c0;
-#pragma unroll 4
-          for (int m = 0; m < 16; ++m) {
-            double ai[4], xv[4];
+        for (int s4 = 0; s4 < 4; ++s4) b[s4] = XT(c0 + 4 * s4 + lc, 8 * J + lr);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) ai[u] = Pi[u * GPC_PD_LD + m];
+        for (int it = 0; it < 2; ++it) {
+          o[it][0] = o[it][1] = 0.0;
+          const int i = 8 * it + lr;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) xv[v] = (c0 + m >= cc + v) ? XT(c0 + m, cc + v) : 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int v = 0; v < 4; ++v) c[u][v] = fma(ai[u], xv[v], c[u][v]);
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int tt = 4 * s4 + lc;
+            const double a = (tt <= i) ? XT(c0 + i, c0 + tt) : 0.0;
+            dmma884(o[it][0], o[it][1], a, b[s4]);
           }
+        }
+        __syncwarp();
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) XT(rr + u, cc + v) -= c[u][v];
+        for (int it = 0; it < 2; ++it) {
+          XT(c0 + 8 * it + lr, 8 * J + 2 * lc) = o[it][0];
+          XT(c0 + 8 * it + lr, 8 * J + 2 * lc + 1) = o[it][1];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (3) rank-16 updates.  Warp 0 takes the three tiles of the next diagonal sub-block and goes on to factor it
+    //      (the serial part of step kb + 1); the other warps share everything else. ---------------------------
+    if (mt > 0) {
+      const int n3a = mt * (mt + 1) / 2, n3b = mt * (r0 >> 3), nj = r0 >> 3;
+      if (warp == 0) {
+        chol_tile(r0, c0, 0, 0);
+        chol_tile(r0, c0, 1, 0);
+        chol_tile(r0, c0, 1, 1);
+        __syncwarp();
+        factor16(r0);
+      } else {
+        for (int idx = 3 + (warp - 1); idx < ((GPC_PD_SKIP & 1) ? 0 : n3a + n3b); idx += GPC_PD_NT / 32 - 1) {
+          if (idx < n3a) {
+            int I = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+            while (I * (I + 1) / 2 > idx) --I;
+            while ((I + 1) * (I + 2) / 2 <= idx) ++I;
+            chol_tile(r0, c0, I, idx - I * (I + 1) / 2);
+          } else {
+            const int e = idx - n3a;
+            inv_tile(r0, c0, e / nj, e % nj);
+          }
         }
       }
     }
     __syncthreads();
   }
   if (bad && tid == 0) atomicCAS(status, 0, p + 1);
+  if (GPC_PD_SKIP & 4) {
+    if (tid == 0) Ap[0] = S[0] + XT(127, 0);
+    return;
+  }
 #pragma unroll 8
   for (int e = tid; e < 128 * 128; e += GPC_PD_NT) {
     const int r = e >> 7, c = e & 127;
@@ -332,28 +321,42 @@ __global__ void __launch_bounds__(256) k_trmv_n(const double* __restrict__ M, lo
   if (i >= n) return;
   const int lane = threadIdx.x & 31;
   const double* row = M + i * ld;
-  double s = 0.0;
-  for (long j = lane; j <= i; j += 32) s = fma(row[j], x[j], s);
-  s = warp_sum(s);
+  // four independent accumulators, eight loads in flight per lane: the loop is latency-, not bandwidth-bound
+  double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  long j = lane;
+  for (; j + 96 <= i; j += 128) {
+    s = fma(row[j], x[j], s);
+    s1 = fma(row[j + 32], x[j + 32], s1);
+    s2 = fma(row[j + 64], x[j + 64], s2);
+    s3 = fma(row[j + 96], x[j + 96], s3);
+  }
+  for (; j <= i; j += 32) s = fma(row[j], x[j], s);
+  s = warp_sum((s + s1) + (s2 + s3));
   if (lane == 0) out[i] = (bias ? bias_scale * bias[i] : 0.0) + sign * s;
 }
 
-__global__ void __launch_bounds__(128) k_trmv_t_partial(const double* __restrict__ M, long ld,
+__global__ void __launch_bounds__(512) k_trmv_t_partial(const double* __restrict__ M, long ld,
                                                         const double* __restrict__ x,
                                                         double* __restrict__ partial, long n_pad) {
+  // 512 threads: column j = threadIdx.x % 128 of the tile, rows split over four thread groups of 32 rows each
+  // (a quarter of the serial chain per thread), combined through shared memory
+  __shared__ double red[3][128];
   const int cb = blockIdx.x, rb = blockIdx.y;
-  const long j = (long)cb * 128 + threadIdx.x;
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const long j = (long)cb * 128 + tx;
   double s = 0.0;
   if (rb >= cb) {
-    const long i0 = (long)rb * 128;
-#pragma unroll 8
-    for (int r = 0; r < 128; ++r) {
+    const long i0 = (long)rb * 128 + 32 * ty;
+#pragma unroll 16
+    for (int r = 0; r < 32; ++r) {
       const long i = i0 + r;
       const double m = M[i * ld + j];
       s = fma((i >= j) ? m : 0.0, x[i], s);
     }
   }
-  partial[(long)rb * n_pad + j] = s;
+  if (ty > 0) red[ty - 1][tx] = s;
+  __syncthreads();
+  if (ty == 0) partial[(long)rb * n_pad + j] = ((s + red[0][tx]) + (red[1][tx] + red[2][tx]));
 }
 
 __global__ void __launch_bounds__(256) k_colsum_partial(const double* __restrict__ partial, int nrb, long n_pad,

@@ -649,6 +649,12 @@ def run_ours(args):
         factor = {"ms": 1e3 * min(tf), "tflops": tfl, "frac_of_dgemm_peak": tfl / dgemm_peak,
                   "flops": "N^3/3 Cholesky + N^3/3 triangular inverse (assembly, alpha, log-det inside the time)"}
 
+    # ---- the factorisation at N = 8192 (configs[2]'s size), both ways of counting: Cholesky + explicit L^-1 as the
+    # product computes it (2 N^3 / 3 flop) and the Cholesky alone (GPC_FACTOR_PHASE=chol, a profiling switch: N^3 / 3)
+    factor_8192 = None
+    if dist is None and args.factor8192:
+        factor_8192 = bench_factor(gpcore, L, torch, local, 8192, dgemm_peak)
+
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------
     cpu = None
     if world == 1:
@@ -672,7 +678,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "mode": args.mode, "other_mode": other,
             "factor_ms": 1e3 * t_factor, "factor_broadcast_ms": 1e3 * t_bcast, "factor_replication": repl,
-            "time_to_first_result_ms": ttfr_ms, "factor": factor,
+            "time_to_first_result_ms": ttfr_ms, "factor": factor, "factor_8192": factor_8192,
             "mean_only": mean_only, "noisy_input": noisy, "parity": parity}
 
     line["ig"] = ig_line
@@ -680,6 +686,41 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_factor(gpcore, L, torch, local, N, dgemm_peak):
+    X4, y = make_train(N, 3, seed=8)
+    X4[:, 3] = 0.0
+    core = gpcore.GPCore(L.KIND_SF_RBF, 1, local)
+    core.set_hypers(np.array([4.0, 2.0, 3.0, 2.5, 0.05]), 1e-8)
+    core.set_data(X4, y)
+    out = {}
+    for phase in ("full", "chol"):
+        if phase == "chol":
+            os.environ["GPC_FACTOR_PHASE"] = "chol"
+        try:
+            core.factor()
+        except Exception:
+            pass                      # chol-only leaves no valid inverse: alpha / log-det of that pass are garbage
+        ts = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            try:
+                core.factor()
+            except Exception:
+                pass
+            ts.append(time.perf_counter() - t0)
+        out[phase] = min(ts)
+        os.environ.pop("GPC_FACTOR_PHASE", None)
+    core.close()
+    n3 = float(N) ** 3 / 3.0
+    return {"n_train": N, "ms": 1e3 * out["full"], "ms_chol_only": 1e3 * out["chol"],
+            "tflops_with_inverse": 2.0 * n3 / out["full"] / 1e12, "frac_with_inverse": 2.0 * n3 / out["full"] / 1e12 / dgemm_peak,
+            "tflops_chol_flops_over_full_time": n3 / out["full"] / 1e12,
+            "tflops_chol_only": n3 / out["chol"] / 1e12, "frac_chol_only": n3 / out["chol"] / 1e12 / dgemm_peak,
+            "note": "assembly, alpha (two triangular solves with one refinement step each) and the log-det are inside both "
+                    "times; ms_chol_only = the same call with the triangular inverse switched off (GPC_FACTOR_PHASE=chol)"}
 
 
 def int8_peaks():
@@ -692,7 +733,7 @@ def int8_peaks():
         return 4341.7, 3774.4, "fallback: the figures profiles/microbench/umma_i8_sustained.cu measured in round 2"
 
 
-def cpu_ig_baseline(N, F, k, grid4, X4, y, rows, offs, n_literal=3, n_schur=256):
+def cpu_ig_baseline(N, F, k, grid4, X4, y, rows, offs, n_literal=3, n_schur=16):
     """The reference's way (calculatePathInfoEmuBatch, PhysicalExperimentCode/GraceRIGV3.py:599-618: one full refit of
     the (N + k)-point model and two G x G determinants per candidate) on a bounded sample, and the Schur-complement
     port of the same quantity, both on the host cores."""
@@ -845,6 +886,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --m-test points PER GPU (default); strong: ONE set of --m-test points split over the GPUs")
     ap.add_argument("--parity", type=int, default=1, help="check the timed results against the CPU oracle (4096 points)")
+    ap.add_argument("--factor8192", type=int, default=1, help="also time the factorisation at N = 8192")
     ap.add_argument("--ig", type=int, default=1)
     ap.add_argument("--ig-candidates", type=int, default=65536)
     args = ap.parse_args()

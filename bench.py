@@ -275,6 +275,12 @@ def apply_workload_defaults(args):
 
 def workload_config(args):
     cfg = _workload_config(args)
+    if args.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        cfg["workload"] += " -- STRONG scaling: --m-test = %d is the size of ONE test set split contiguously over %d GPU(s)" \
+                           % (args.m_test, world)
+        cfg["m_test_total"] = args.m_test
+        cfg["m_test_per_gpu"] = args.m_test // world
     cfg["variance_path"] = ("int8: Ozaki splitting, 6 base-256 digits per operand, 21 exact digit GEMMs on the tcgen05 INT8 "
                             "tensor cores, FP64 results to ~1e-12 (parity tolerance 1e-9)") if args.mode == "int8" \
         else "fp64: DMMA (mma.sync.m8n8k4.f64)"

@@ -86,6 +86,10 @@ def warm_up(group=None):
     dist.all_reduce(t, group=group)
     dist.broadcast(t, 0, group=group)
     if dev != "cpu":
+        # large messages take another protocol / more channels than a 4-byte one: connect those too
+        big = torch.empty(8 << 20, dtype=torch.float64, device=dev)
+        dist.broadcast(big, 0, group=group)
+        dist.broadcast(big, 0, group=group)
         torch.cuda.synchronize()
 
 

@@ -404,6 +404,11 @@ def run_ours(args):
     core.predict_dev(dXs.data_ptr(), m_first, dmean.data_ptr(), dvar.data_ptr(), flags)
     torch.cuda.synchronize()
     ttfr_ms = 1e3 * (time.perf_counter() - t0)
+    if repl["mode"].startswith("broadcast"):
+        # the same replication once more (staging buffers of the bands now cached by the allocator): steady state
+        dist.barrier()
+        again = replicate_factor(core, 0)
+        repl["steady_ms"], repl["steady_gbps"], repl["steady_factor_ms"] = again["ms"], again["gbps"], again["factor_ms"]
     if dist is not None:
         t = torch.tensor([ttfr_ms, repl["ms"], repl["factor_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -624,3 +624,117 @@ def test_out_of_range_fidelity_is_rejected_everywhere(gpcore_mod):
     for call in (w.predict, w.predict_covariance, k.K):
         with pytest.raises(ValueError, match="fidelity"):
             call(bad)
+
+
+def _inv_sym3(A):
+    """Cofactor inverse of a 3 x 3 matrix, plain Python floats (no LAPACK, no oracle)."""
+    (a, b, c), (d, e, f), (g, h, i) = A
+    det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)
+    return [[(e * i - f * h) / det, (c * h - b * i) / det, (b * f - c * e) / det],
+            [(f * g - d * i) / det, (a * i - c * g) / det, (c * d - a * f) / det],
+            [(d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det]], det
+
+
+def test_ar1_closed_form_known_answers(gpcore_mod):
+    """Known-answer test of the AR1 (Kennedy-O'Hagan) multi-fidelity posterior that does NOT go through
+    oracle/gp_oracle.py: one training point per fidelity (F = 3), every quantity written out by hand from
+        K[(x,i),(x',j)] = sum_{m <= min(i,j)} (prod_{l=m}^{i-1} rho_l)(prod_{l=m}^{j-1} rho_l) k_m(x, x'),
+        k_m(x, x') = v_m exp(-1/2 sum_d ((x_d - x'_d) / l_md)^2),
+    per-fidelity noise and GPy's 1e-8 jitter on the training diagonal; the 3 x 3 system is inverted by cofactors in
+    plain Python.  Checks kern.K, predict (mean, noise-inclusive variance at each fidelity), predict_covariance
+    (with emukit's 1e-10 clip) and the NLML."""
+    import math
+    from gpcore.GPy.kern import RBF
+    from gpcore.emukit.multi_fidelity.kernels import LinearMultiFidelityKernel
+    from gpcore.emukit.multi_fidelity.models import GPyLinearMultiFidelityModel
+    from gpcore.emukit.model_wrappers.gpy_model_wrappers import GPyMultiOutputWrapper
+    v = [2.0, 0.7, 0.3]
+    ls = [[1.5, 2.0, 1.0], [0.8, 1.1, 0.9], [2.5, 0.6, 1.7]]
+    rho = [0.8, 1.3]
+    noise = [0.05, 0.02, 0.01]
+    X = [[0.3, 1.0, 0.5], [0.9, 0.4, 0.2], [0.1, 0.7, 1.1]]       # training point of fidelity 0, 1, 2
+    y = [0.7, -0.4, 1.2]
+    xs = [[0.5, 0.8, 0.6], [0.2, 0.5, 0.9]]                        # two test locations
+
+    def kb(m, a, b):
+        return v[m] * math.exp(-0.5 * sum(((a[d] - b[d]) / ls[m][d]) ** 2 for d in range(3)))
+
+    def coef(i, m):
+        c = 1.0
+        for l in range(m, i):
+            c *= rho[l]
+        return c
+
+    def k(a, i, b, j):
+        return sum(coef(i, m) * coef(j, m) * kb(m, a, b) for m in range(min(i, j) + 1))
+
+    Ky = [[k(X[i], i, X[j], j) + ((noise[i] + 1e-8) if i == j else 0.0) for j in range(3)] for i in range(3)]
+    Kinv, det = _inv_sym3(Ky)
+    alpha = [sum(Kinv[i][j] * y[j] for j in range(3)) for i in range(3)]
+    nlml = 0.5 * sum(y[i] * alpha[i] for i in range(3)) + 0.5 * math.log(det) + 1.5 * math.log(2 * math.pi)
+
+    kern = LinearMultiFidelityKernel([RBF(3, ARD=True) for m in range(3)])
+    X4 = np.array([X[i] + [float(i)] for i in range(3)])
+    model = GPyLinearMultiFidelityModel(X4, np.array(y)[:, None], kern, n_fidelities=3)
+    # param_array order pinned by PhysicalExperimentCode/...MFGP.py:670: (var, l(3)) x 3, rho1, rho2, noise x 3
+    model.param_array[:] = np.concatenate([[v[0]], ls[0], [v[1]], ls[1], [v[2]], ls[2], rho, noise])
+    w = GPyMultiOutputWrapper(model, 3, 1)
+    Kdev = kern.K(X4)
+    for i in range(3):
+        for j in range(3):
+            assert abs(Kdev[i, j] - k(X[i], i, X[j], j)) < 1e-13
+    assert abs(model.objective_function() - nlml) < 1e-10 * max(1.0, abs(nlml))
+    T4 = np.array([xs[t] + [float(f)] for t in range(2) for f in range(3)])
+    mu, var = w.predict(T4)
+    for r, (t, f) in enumerate((t, f) for t in range(2) for f in range(3)):
+        ks = [k(xs[t], f, X[j], j) for j in range(3)]
+        m_want = sum(ks[j] * alpha[j] for j in range(3))
+        v_want = k(xs[t], f, xs[t], f) - sum(ks[i] * Kinv[i][j] * ks[j] for i in range(3) for j in range(3)) + noise[f]
+        assert abs(mu[r, 0] - m_want) < 1e-12 * max(1.0, abs(m_want)), (r, mu[r, 0], m_want)
+        assert abs(var[r, 0] - v_want) < 1e-12 * max(1.0, v_want), (r, var[r, 0], v_want)
+    C = w.predict_covariance(T4)
+    for a, (ta, fa) in enumerate((t, f) for t in range(2) for f in range(3)):
+        for b, (tb, fb) in enumerate((t, f) for t in range(2) for f in range(3)):
+            ka = [k(xs[ta], fa, X[j], j) for j in range(3)]
+            kbv = [k(xs[tb], fb, X[j], j) for j in range(3)]
+            want = k(xs[ta], fa, xs[tb], fb) - sum(ka[i] * Kinv[i][j] * kbv[j] for i in range(3) for j in range(3))
+            if a == b:
+                want += noise[fa]
+            want = max(want, 1e-10)                                   # emukit: np.clip(cov, 1e-10, inf)
+            assert abs(C[a, b] - want) < 1e-12 * max(1.0, abs(want)), (a, b, C[a, b], want)
+
+
+def test_gptrainers_flow_on_twelve_bundled_datasets(gpcore_mod):
+    """BASELINE configs[0] widened: the reference's GPTrainers.py flow on twelve bundled data sets of field 0
+    (tests/golden/gp_datasets.npz) against the numbers the reference published for each
+    (Data/TrajectoriesAndEstimates/GPResults/MSE_*.txt, produced with real GPy / emukit): the single- and multi-fidelity
+    RMSEs inside a 1e-4 band, the single-fidelity covariance-weighted MSEs inside 1e-3 (they depend on where the
+    reference's unseeded optimisers stopped, so this is a band, not a pin; the NIGP number moves with the reference's
+    unseeded restarts and is only required to stay inside 5 %)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("gptrainers_flow", os.path.join(ROOT, "examples", "gptrainers_flow.py"))
+    flow = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(flow)
+    g = golden("gp_datasets.npz")
+    cn = [str(c) for c in g["columns"]]
+    Lsw = g["field0_Lsw"]
+    field = dict(L=Lsw[0], s=Lsw[1], w=Lsw[2:], p=g["field0_p"])
+    worst = {"mf": 0.0, "sf": 0.0, "sfTP": 0.0, "nisf": 0.0, "w_sf": 0.0, "w_sfTP": 0.0}
+    for name in [str(n) for n in g["names"]]:
+        d = g["data_" + name]
+        d = d[d[:, 0] < 3600]                                        # GPTrainers.py:37
+        cols = {c: d[:, i] for i, c in enumerate(cn)}
+        np.random.seed(0)
+        rm, wm = flow.run(cols, field=field, verbose=False)
+        pub = dict(zip(("mf", "sf", "nisf", "sfTP", "w_mf", "w_sf", "w_nisf", "w_sfTP"), g["pub_" + name]))
+        for kk in ("mf", "sf", "sfTP", "nisf"):
+            worst[kk] = max(worst[kk], abs(rm[kk] - pub[kk]) / pub[kk])
+        for kk in ("sf", "sfTP"):
+            if np.isfinite(wm[kk]):
+                worst["w_" + kk] = max(worst["w_" + kk], abs(float(wm[kk]) - pub["w_" + kk]) / pub["w_" + kk])
+    print("worst relative deviation from the published numbers over 12 data sets:", worst)
+    assert worst["mf"] < 1e-4 and worst["sf"] < 1e-4 and worst["sfTP"] < 1e-4, worst
+    assert worst["nisf"] < 5e-2, worst
+    assert worst["w_sf"] < 1e-3 and worst["w_sfTP"] < 1e-3, worst

@@ -12,7 +12,7 @@ for name in [str(n) for n in g["names"]]:
     d = g["data_" + name]
     d = d[d[:, 0] < 3600]
     cols = {c: d[:, i] for i, c in enumerate(cols_names)}
-    fid = int(name.split("_")[2])
+    fid = 0
     Lsw = g["field%d_Lsw" % fid]
     field = dict(L=Lsw[0], s=Lsw[1], w=Lsw[2:], p=g["field%d_p" % fid])
     np.random.seed(0)

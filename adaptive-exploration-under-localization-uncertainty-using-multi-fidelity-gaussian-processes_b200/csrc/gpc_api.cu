@@ -666,6 +666,8 @@ int gpc_version(void) { return GPC_VERSION; }
 
 const char* gpc_last_error(gpc_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static void destroy_handle(gpc_handle h);
+
 int gpc_create(int kind, int F, int device, gpc_handle* out) {
   gpc_handle h = nullptr;
   if (!out) return fail(nullptr, GPC_ERR_ARG, "out == NULL");
@@ -713,24 +715,23 @@ int gpc_create(int kind, int F, int device, gpc_handle* out) {
   }
   if (e != cudaSuccess) {
     std::string m = cudaGetErrorString(e);
-    delete h;
+    destroy_handle(h);            // streams / events created so far
     return fail(nullptr, GPC_ERR_CUDA, m);
   }
   int rc = set_gemm_attrs(h);
   if (rc) {
     g_create_error = h->err;
-    cudaStreamDestroy(h->stream);
-    delete h;
+    destroy_handle(h);
     return rc;
   }
   *out = h;
   return GPC_OK;
 }
 
-int gpc_destroy(gpc_handle h) {
-  if (!h) return GPC_OK;
+// Releases everything a handle owns; safe on a partially constructed handle (every member starts as nullptr).
+static void destroy_handle(gpc_handle h) {
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->gmT, &h->gmA, &h->gmC, &h->gmc, &h->gmax, &h->gmmean, &h->Vimg, &h->gBimg, &h->gsB, &h->sV1, &h->Pt, &h->Xt, &h->y, &h->extra, &h->L, &h->X, &h->T, &h->alpha, &h->vec, &h->partial, &h->scal,
                     &h->status, &h->Wm, &h->gpart, &h->Xs4, &h->Kx, &h->meanpart, &h->sumsq, &h->gradpart, &h->mean, &h->var, &h->Vt,
                     &h->cov, &h->grads, &h->ediag, &h->Bimg, &h->sBv, &h->Aimg, &h->Aimg2, &h->meanpart2, &h->gradpart2, &h->gX4, &h->gVt, &h->gS, &h->gSinv, &h->gT, &h->Bt, &h->Zt,
@@ -757,8 +758,13 @@ int gpc_destroy(gpc_handle h) {
   if (h->ev_inv) cudaEventDestroy(h->ev_inv);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->inv) cudaStreamDestroy(h->inv);
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+int gpc_destroy(gpc_handle h) {
+  if (!h) return GPC_OK;
+  destroy_handle(h);
   return GPC_OK;
 }
 

@@ -268,9 +268,10 @@ class InfoGainOperators:
             self.logDetPrior = ldp if LOG_DBL_MIN <= ldp <= LOG_DBL_MAX else (fallback if ldp < LOG_DBL_MIN else np.inf)
         return _guarded_sf_batch(I_raw, ldp, G, fallback)
 
-    # True: the single-path ``calcPathInfoSFBatch`` reproduces the reference's cached model copy, whose data
-    # GROW across the calls of one ``plan()`` (see there).  The batched ``*_many`` / ``score_many`` calls always
-    # score every path against the agent's current data only.
+    # True: the single-path ``calcPathInfoSFBatch`` / ``calculatePathInfoEmuBatch`` reproduce the reference's cached
+    # model copies ``sfgp2`` / ``mfgp2``: made once, they keep the HYPER-PARAMETERS of that moment, and the SF copy's
+    # data GROW across the calls of one ``plan()`` (see there).  The batched ``*_many`` / ``score_many`` calls always
+    # score every path against the agent's current model and data only.
     reference_quirks = True
 
     def calcPathInfoSFBatch(self, V, E, path, dense=True):
@@ -319,7 +320,25 @@ class InfoGainOperators:
         return np.asarray(I_raw)
 
     def calculatePathInfoEmuBatch(self, V, E, path, dense=False):
-        return float(self.calculatePathInfoEmuBatch_many(V, E, [path], dense)[0])
+        """``Phys/GraceRIGV3.py:599-618``.  The reference scores on a cached copy ``mfgp2`` made the first time the
+        operator runs (``:608-609``): its DATA are reset to the agent's on every call (``:611``) but its
+        HYPER-PARAMETERS stay the ones the agent's model had when the copy was made, and ``logDetPrior`` is the one of
+        the first call of the ``plan()``.  With ``reference_quirks`` (default) both are reproduced; otherwise (and in
+        the batched ``*_many`` / ``score_many`` calls) the agent's current model is used."""
+        if not self.reference_quirks:
+            return float(self.calculatePathInfoEmuBatch_many(V, E, [path], dense)[0])
+        m = getattr(self, "_mfb_model", None)
+        if m is None:
+            m = self._mfb_model = self.mfgp.copy()
+        m.set_data(self.mfgp.X, self.mfgp.Y)
+        pts = self._mf_points(V, E, path, dense, bounded_top=True)
+        grid = np.asarray(self.fieldGrid, dtype=float)
+        grid4 = np.hstack([grid[:, :3], 2 * np.ones((grid.shape[0], 1))])
+        I_raw, ldp, _ = logdet_info_gain(m, grid4, [pts], clip=True)
+        if self.logDetPrior is None:
+            self.logDetPrior = ldp
+        # I = 1/2 (logDetPrior - logdet posterior), the posterior log-det recovered from the raw gain
+        return float(I_raw[0] + 0.5 * (self.logDetPrior - ldp))
 
     def calculatePathInfoEmu2_many(self, V, E, paths, dense=False):
         """``GraceRIGV3.py:505-523``: grid = the candidate's own points at fidelity 2, prior = the

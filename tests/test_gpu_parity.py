@@ -607,6 +607,21 @@ def test_ig_agent_operators(gpcore_mod, go):
             q = X[i:i + 1].copy(); q[0, 3] = 0
             tot += np.log(1 + tmp.predict(q)[1][0, 0] / MF_PARAMS[-1])
         assert abs(Iw[ci] - tot) < 1e-8 * abs(tot), (ci, Iw[ci], tot)
+    # reference quirk (PhysicalExperimentCode/GraceRIGV3.py:608-611): the single-path operator scores on a cached copy
+    # mfgp2 whose DATA follow the agent but whose HYPER-PARAMETERS stay those of the moment the copy was made
+    ag.logDetPrior = None
+    first = ag.calculatePathInfoEmuBatch(None, E, paths[0])
+    assert abs(first - Jm[0]) < 1e-9 * max(1.0, abs(Jm[0]))
+    p_new = MF_PARAMS.copy()
+    p_new[0] *= 1.7
+    p_new[-1] *= 2.0
+    ag.mfgp.gpy_model.param_array[:] = p_new
+    stale = ag.calculatePathInfoEmuBatch(None, E, paths[1])
+    assert abs(stale - Jm[1]) < 1e-9 * max(1.0, abs(Jm[1]))          # the copy still has the old hyper-parameters
+    ag.reference_quirks = False
+    ag.logDetPrior = None
+    fresh = ag.calculatePathInfoEmuBatch(None, E, paths[1])
+    assert abs(fresh - stale) > 1e-4                                  # the agent's current model differs
 
 
 def test_hot_kernel_timing_hooks(gpcore_mod):

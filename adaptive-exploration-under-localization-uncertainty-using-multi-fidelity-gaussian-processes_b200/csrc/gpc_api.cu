@@ -172,10 +172,14 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_ig_selfgrid_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_IG_SMEM));
   CK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, GPC_POTRF_SMEM));
   CK(cudaFuncSetAttribute(k_gm_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device));
   return GPC_OK;
 }
@@ -458,6 +462,9 @@ double v_scale(gpc_handle h) {
   return kmax > 0.0 ? std::sqrt(kmax) * gpoz::SCALE_HEADROOM : 1.0;  // |V| / sV <= 0.4975
 }
 
+// Digit levels of the INT8 contraction: 6 (21 digit GEMMs, FP64 results) or 4 in the FP32-tolerance mode (10 GEMMs).
+inline int i8_levels(gpc_handle h) { return h->mode == GPC_MODE_INT8_F32 ? 4 : gpoz::S; }
+
 template <int OUT, bool FULLK>
 int launch_i8(gpc_handle h, const VtI8Args& a, double fp64_equiv_flops) {
   const int grid = a.n_items < h->n_sm ? a.n_items : h->n_sm;
@@ -474,7 +481,8 @@ int launch_i8(gpc_handle h, const VtI8Args& a, double fp64_equiv_flops) {
     e1 = h->ev[h->ev_used++];
     CK(cudaEventRecord(e0, h->stream));
   }
-  k_vt_i8<OUT, FULLK><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
+  if (a.nlev == gpoz::S) k_vt_i8<OUT, FULLK, gpoz::S><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
+  else k_vt_i8<OUT, FULLK, 4><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
   CKL();
   if (h->hot_timing) {
     CK(cudaEventRecord(e1, h->stream));
@@ -507,6 +515,7 @@ int launch_vt_i8(gpc_handle h, const int8_t* Aimg, long m_pad, double* Vt, doubl
   a.nkb_out = a.nkb;
   a.dig_mul = gpoz::DIGIT_MUL / v_scale(h);
   a.sumsq = sumsq;
+  a.nlev = i8_levels(h);
   return launch_i8<OUT, false>(h, a, (double)m_pad * (double)np * (double)(np + 64));
 }
 
@@ -529,6 +538,7 @@ int launch_gram_i8(gpc_handle h, const int8_t* Vimg, long m_pad, const double* s
   a.m_pad = m_pad;
   a.n_items = (int)(m_pad / gpoz::TM) * 2;
   a.out = gram;
+  a.nlev = i8_levels(h);
   return launch_i8<OUT_F64, true>(h, a, (double)m_pad * 128.0 * (double)np);
 }
 
@@ -551,6 +561,7 @@ int launch_cross_i8(gpc_handle h, const int8_t* Vimg, long m_pad, const int8_t* 
   a.m_pad = m_pad;
   a.n_items = (int)(m_pad / gpoz::TM) * a.nb2;
   a.out = P;
+  a.nlev = i8_levels(h);
   return launch_i8<OUT_F64, true>(h, a, (double)m_pad * (double)g_pad * (double)np);
 }
 
@@ -616,7 +627,7 @@ int predict_i8_pipeline(gpc_handle h, const double* dXs4, long M, double* dmean,
 }
 
 inline bool use_i8(gpc_handle h, const double* dvar, unsigned flags) {
-  return dvar && !(flags & GPC_MEAN_ONLY) && h->mode == GPC_MODE_INT8 && h->n_pad <= gpoz::MAX_K;
+  return dvar && !(flags & GPC_MEAN_ONLY) && h->mode != GPC_MODE_FP64 && h->n_pad <= gpoz::MAX_K;
 }
 
 // One chunk of the posterior on the FP64 path (device pointers; M <= m_chunk).  d_sx != NULL adds
@@ -1481,7 +1492,7 @@ long gpc_launch_count(gpc_handle h) { return h ? h->launches : 0; }
 
 int gpc_set_mode(gpc_handle h, int mode) {
   if (!h) return GPC_ERR_ARG;
-  if (mode != GPC_MODE_FP64 && mode != GPC_MODE_INT8) return fail(h, GPC_ERR_ARG, "unknown mode");
+  if (mode != GPC_MODE_FP64 && mode != GPC_MODE_INT8 && mode != GPC_MODE_INT8_F32) return fail(h, GPC_ERR_ARG, "unknown mode");
   h->mode = mode;
   return GPC_OK;
 }

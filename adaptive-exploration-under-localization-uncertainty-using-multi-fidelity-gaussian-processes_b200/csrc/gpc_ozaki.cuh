@@ -347,6 +347,9 @@ struct VtI8Args {
   int nkb_out;
   double dig_mul;             // 2^48 / (scale of the emitted digits)
   double* sumsq;              // OUT_SUMSQ
+  int nlev;                   // digit levels used (= the kernel's NLEV template argument): 6 = full (21 digit GEMMs, FP64
+                              // results), 4 = FP32-tolerance mode (pairs p + q <= 3: 10 GEMMs); the unused low-order slices
+                              // are neither copied nor multiplied
 };
 
 template <bool FULLK>
@@ -365,7 +368,7 @@ __device__ __forceinline__ void vt_item(int item, int nb2, int npair, int& mt, i
   }
 }
 
-template <int OUT, bool FULLK>
+template <int OUT, bool FULLK, int NLEV>
 __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ VtI8Args a) {
   using namespace gpoz;
   extern __shared__ uint8_t smem_raw[];
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
   const long m_pad = a.m_pad;
   const double sA = a.sA;
   const double* __restrict__ sB = a.sB;
+  constexpr int nlev = NLEV;   // compile-time: the MMA issue loop of the one issuing thread must unroll completely
 
   if (tid == 0) {
 #pragma unroll
@@ -412,14 +416,15 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
             const int st = it % STAGES;
             if (it >= STAGES) mbar_wait_guarded(&empty_bar[st], ((it / STAGES) - 1) & 1);
             uint8_t* dst = smem + st * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[st], STAGE_BYTES);
-            tma_bulk_g2s(dst, a.Aimg + (((long)mt * nkb_total + kb) * S) * (long)A_SLICE, A_STAGE, &full_bar[st]);
+            // slice p of a k-block is the p-th most significant digit: the first nlev slices are a contiguous prefix
+            mbar_expect_tx(&full_bar[st], (uint32_t)nlev * (A_SLICE + B_SLICE));
+            tma_bulk_g2s(dst, a.Aimg + (((long)mt * nkb_total + kb) * S) * (long)A_SLICE, (uint32_t)nlev * A_SLICE, &full_bar[st]);
             const int8_t* bsrc = a.Bimg + (long)mt * a.b_mt + (long)jb * a.b_j + (long)kb * a.b_k;
             if (a.b_p == (long)B_SLICE) {
-              tma_bulk_g2s(dst + A_STAGE, bsrc, B_STAGE, &full_bar[st]);
+              tma_bulk_g2s(dst + A_STAGE, bsrc, (uint32_t)nlev * B_SLICE, &full_bar[st]);
             } else {
 #pragma unroll
-              for (int p = 0; p < S; ++p) tma_bulk_g2s(dst + A_STAGE + p * B_SLICE, bsrc + (long)p * a.b_p, B_SLICE, &full_bar[st]);
+              for (int p = 0; p < nlev; ++p) tma_bulk_g2s(dst + A_STAGE + p * B_SLICE, bsrc + (long)p * a.b_p, B_SLICE, &full_bar[st]);
             }
           }
         }
@@ -453,10 +458,10 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-              for (int pp = 0; pp < S; ++pp) {
+              for (int pp = 0; pp < nlev; ++pp) {
                 int q0 = 0;
-                while (q0 < S - pp) {
-                  const int nsl = (S - pp - q0) > 4 ? 4 : (S - pp - q0);  // slices in this MMA (N <= 256)
+                while (q0 < nlev - pp) {
+                  const int nsl = (nlev - pp - q0) > 4 ? 4 : (nlev - pp - q0);  // slices in this MMA (N <= 256)
                   const uint32_t idesc = idesc0 | ((uint32_t)((nsl * TN) >> 3) << 17);
                   umma_i8(tmem_base + (pp + q0) * TN, umma_desc(sa + pp * A_SLICE + kk * 256),
                           umma_desc(sb + q0 * B_SLICE + kk * 256), idesc, (kb > 0 || kk > 0 || pp > 0) ? 1u : 0u);
@@ -504,13 +509,22 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cend; c0 += 8) {
           tmem_wait3(v0, v1, v2);
-          tmem_ld8(lane_addr + 3 * TN + c0, w0);
-          tmem_ld8(lane_addr + 4 * TN + c0, w1);
-          tmem_ld8(lane_addr + 5 * TN + c0, w2);
+          // levels >= nlev were never accumulated (their TMEM columns hold stale data): they count as zero
+          if (nlev > 3) tmem_ld8(lane_addr + 3 * TN + c0, w0);
+          if (nlev > 4) tmem_ld8(lane_addr + 4 * TN + c0, w1);
+          if (nlev > 5) tmem_ld8(lane_addr + 5 * TN + c0, w2);
           long long hi[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) hi[j] = (long long)v0[j] * 65536LL + (long long)v1[j] * 256LL + (long long)v2[j];
           tmem_wait3(w0, w1, w2);
+          if (nlev <= 5) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              w2[j] = 0;
+              if (nlev <= 4) w1[j] = 0;
+              if (nlev <= 3) w0[j] = 0;
+            }
+          }
           if (c0 + 8 < cend) {
             tmem_ld8(lane_addr + 0 * TN + c0 + 8, v0);
             tmem_ld8(lane_addr + 1 * TN + c0 + 8, v1);

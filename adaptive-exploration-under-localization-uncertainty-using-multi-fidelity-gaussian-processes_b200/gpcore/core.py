@@ -237,7 +237,8 @@ class GPCore:
         return int(self.lib.gpc_launch_count(self.h))
 
     def set_mode(self, mode):
-        """``_lib.MODE_INT8`` (default: tcgen05 INT8 Ozaki contraction) or ``_lib.MODE_FP64`` (DMMA)."""
+        """``_lib.MODE_INT8`` (default: tcgen05 INT8 Ozaki contraction, FP64 results), ``_lib.MODE_FP64`` (DMMA) or
+        ``_lib.MODE_INT8_F32`` (the optional FP32-tolerance mode: 4 of the 6 digits, 10 of the 21 digit GEMMs)."""
         self._ck(self.lib.gpc_set_mode(self.h, int(mode)))
 
     def mode(self):

@@ -612,6 +612,15 @@ def run_ours(args):
             torch.cuda.synchronize()
             oms = timed(step_dev, 2, 0)
             other = {"mode": "fp64" if args.mode == "int8" else "int8", "value": M * 2 / (oms * 1e-3), "ms_per_step": oms / 2}
+            # the optional FP32-tolerance mode of the north star (4 of the 6 digits: 10 digit GEMMs), context only
+            core.set_mode(L.MODE_INT8_F32)
+            for _ in range(2):
+                step_dev()
+            torch.cuda.synchronize()
+            fms = timed(step_dev, 3, 0)
+            other["int8_f32_tolerance_mode"] = {"value": M * 3 / (fms * 1e-3), "ms_per_step": fms / 3,
+                                                "note": "GPC_MODE_INT8_F32: variances to ~1e-7 relative (north_star allows 1e-4 "
+                                                        "for an optional FP32 mode); NOT the headline metric"}
             core.set_mode(mode)
         except Exception as exc:   # context only
             other = {"error": str(exc)}

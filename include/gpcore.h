@@ -63,6 +63,13 @@ enum gpc_kind {
  *                  Used for N <= 16384 (int32 accumulator range); larger problems run in FP64. */
 #define GPC_MODE_FP64 0
 #define GPC_MODE_INT8 1
+/*   GPC_MODE_INT8_F32  the optional reduced-precision mode of the north star ("1e-4 for an optional FP32 mode"): the same
+ *                  INT8 contraction with only the 4 most significant digits of each operand (digit pairs p + q <= 3:
+ *                  10 digit GEMMs instead of 21, the low-order slices are neither copied nor multiplied).  Balanced
+ *                  digits truncate to nearest, so the results carry ~2^-30 of the operand scales: variances to ~1e-7
+ *                  relative -- three orders inside an FP32 evaluation of the same cancellation-prone difference --
+ *                  at about half the contraction time.  The mean is unaffected (it is formed in FP64 either way). */
+#define GPC_MODE_INT8_F32 2
 
 /* gpc_ig_seq flags */
 #define GPC_IG_FIRST_PREADDED 1u /* GraceRIGV3.py:454-455: point 0 is appended before it is predicted */

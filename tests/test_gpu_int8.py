@@ -206,3 +206,43 @@ def test_host_predict_stages(gpcore_mod, go):
     mu, var = ref.predict(Xs4[probes, :3])
     assert normwise(m[probes], mu[:, 0]) < TOL and normwise(v[probes], var[:, 0], SF_PARAMS[0]) < TOL
     core.close()
+
+
+def test_fp32_tolerance_mode(gpcore_mod, go):
+    """north_star's optional reduced-precision mode ("1e-4 for an optional FP32 mode"): GPC_MODE_INT8_F32 uses the four
+    most significant digits of each operand (10 of the 21 digit GEMMs).  Posterior and information gain against the
+    oracle at the stated 1e-4; the measured error (~1e-7: balanced digits truncate to nearest) is asserted two orders
+    inside it.  The mean is formed in FP64 in every mode."""
+    L_ = gpcore_mod._lib
+    rng = np.random.default_rng(4242)
+    N, F, M = 1500, 3, 6000
+    X4, y = synth(rng, N, F)
+    core = gpcore_mod.GPCore(L_.KIND_MF_AR1_RBF, F, 0)
+    core.set_hypers(MF_PARAMS, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    Xs4 = np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (M, 3)), rng.integers(0, F, (M, 1)).astype(float)])
+    Xs4[:700, :3] = X4[:700, :3] + 1e-3
+    ref = go.MFGP(X4, y, MF_PARAMS, F=F, gram=False)
+    mu, var = ref.predict(Xs4)
+    flags = L_.INCLUDE_NOISE | L_.CLIP_DIAG
+    core.set_mode(L_.MODE_INT8_F32)
+    assert core.mode() == L_.MODE_INT8_F32
+    m1, v1 = core.predict(Xs4, flags)
+    em, ev = normwise(m1, mu[:, 0]), normwise(v1, var[:, 0], 4.64)
+    print("INT8_F32 posterior: normwise mean %.2e var %.2e, element-wise var %.2e" % (em, ev, np.max(np.abs(v1 - var[:, 0]) / var[:, 0])))
+    assert em < TOL                                  # FP64 mean
+    assert ev < 1e-6 and np.max(np.abs(v1 - var[:, 0]) / var[:, 0]) < 1e-4
+    cands = [np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (k, 3)), rng.integers(0, F, (k, 1)).astype(float)]) for k in (5, 32, 17, 9)]
+    rows, offs = gpcore_mod.GPCore._ragged(cands)
+    g4 = np.hstack([rng.uniform([0, 0, 0], [10, 20, 10], (120, 3)), 2 * np.ones((120, 1))])
+    I, _ = core.ig_seq(rows, offs, float(MF_PARAMS[-1]), pred_fid=0)
+    J, _, _ = core.ig_logdet(g4, rows, offs)
+    I0 = np.array([go.ig_seq_mf_refit(ref, c, float(MF_PARAMS[-1]), 0) for c in cands])
+    J0 = np.array([go.ig_logdet_refit(ref, g4, c) for c in cands])
+    print("INT8_F32 information gain: seq %.2e log-det %.2e" % (normwise(I, I0), normwise(J, J0, 1.0)))
+    assert normwise(I, I0) < 1e-4 and normwise(J, J0, 1.0) < 1e-4
+    core.set_mode(L_.MODE_INT8)                      # and back: the full-precision path is untouched
+    m2, v2 = core.predict(Xs4, flags)
+    assert normwise(v2, var[:, 0], 4.64) < TOL
+    core.close()

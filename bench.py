@@ -563,7 +563,7 @@ def run_ours(args):
         pass
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same config only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01",
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02" if args.mode == "int8" else "r01",
                                          "k_vt_i8_traffic.json" if args.mode == "int8" else "k_vt_traffic.json")))
         if tr["n_train"] == N and tr["chunk_rows"] == args.chunk and not nigp_mode:
             traffic = tr["dram_bytes_per_launch"]

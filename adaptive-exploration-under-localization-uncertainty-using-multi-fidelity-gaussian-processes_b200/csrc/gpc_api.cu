@@ -157,8 +157,9 @@ inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int set_gemm_attrs(gpc_handle h) {
   const int sm = gpcg::SMEM_BYTES;
-  CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_syrk_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES_DEEP));
+  CK(cudaFuncSetAttribute(k_syrk_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_syrk_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES_DEEP));
   CK(cudaFuncSetAttribute(k_linv_level, cudaFuncAttributeMaxDynamicSharedMemorySize, gpc64::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpvt::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpvt::SMEM_BYTES));
@@ -207,9 +208,9 @@ int factor_matrix_launch(gpc_handle h, double* A, double* X, double* T, long n_p
   for (int p = 0; p + 1 < nb; p += 2) {
     cudaStream_t sc = (p == 0) ? s : s2;   // the stream that factored diagonal block p carries the pair's chain
     const int m = nb - p - 1;              // block rows below diagonal block p
-    k_trsm_panel<<<2 * m, gpc64::NT, gpc64::SMEM_BYTES, sc>>>(A, X, n_pad, p, 2 * (p + 1));
+    k_trsm_panel<<<2 * m, gpc64::NT, gpc64::SMEM_BYTES_DEEP, sc>>>(A, X, n_pad, p, 2 * (p + 1));
     CKL();
-    k_syrk_panel<<<dim3(2, 2 * m), gpc64::NT, gpc64::SMEM_BYTES, sc>>>(A, n_pad, p, 2 * (p + 1), 2 * (p + 1), 128);
+    k_syrk_panel<true><<<dim3(2, 2 * m), gpc64::NT, gpc64::SMEM_BYTES_DEEP, sc>>>(A, n_pad, p, 2 * (p + 1), 2 * (p + 1), 128);
     CKL();
     k_potrf_diag<<<1, GPC_PD_NT, GPC_POTRF_SMEM, sc>>>(A, X, n_pad, p + 1, d_status);
     CKL();
@@ -221,7 +222,7 @@ int factor_matrix_launch(gpc_handle h, double* A, double* X, double* T, long n_p
       }
       break;
     }
-    k_trsm_panel<<<2 * m2, gpc64::NT, gpc64::SMEM_BYTES, sc>>>(A, X, n_pad, p + 1, 2 * (p + 2));
+    k_trsm_panel<<<2 * m2, gpc64::NT, gpc64::SMEM_BYTES_DEEP, sc>>>(A, X, n_pad, p + 1, 2 * (p + 2));
     CKL();
     if (early && p + 2 == half) {
       // block columns 0 .. half-1 of L are final: invert the leading half and form T[B, A] = L[B, A] X[A, A]
@@ -244,7 +245,7 @@ int factor_matrix_launch(gpc_handle h, double* A, double* X, double* T, long n_p
     }
     // rank-256 update with panels p, p+1: the next pair's two block columns first ...
     const int la = m2 < 2 ? m2 : 2;
-    k_syrk_panel<<<dim3(2 * la, 2 * m2), gpc64::NT, gpc64::SMEM_BYTES, s>>>(A, n_pad, p, 2 * (p + 2), 2 * (p + 2), 256);
+    k_syrk_panel<true><<<dim3(2 * la, 2 * m2), gpc64::NT, gpc64::SMEM_BYTES_DEEP, s>>>(A, n_pad, p, 2 * (p + 2), 2 * (p + 2), 256);
     CKL();
     CK(cudaEventRecord(h->ev_main, s));
     CK(cudaStreamWaitEvent(s2, h->ev_main, 0));
@@ -252,7 +253,7 @@ int factor_matrix_launch(gpc_handle h, double* A, double* X, double* T, long n_p
     CKL();
     // ... then the rest, concurrently with the next pair's chain
     if (m2 > la) {
-      k_syrk_panel<<<dim3(2 * (m2 - la), 2 * (m2 - la)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(
+      k_syrk_panel<false><<<dim3(2 * (m2 - la), 2 * (m2 - la)), gpc64::NT, gpc64::SMEM_BYTES, s>>>(
           A, n_pad, p, 2 * (p + 2 + la), 2 * (p + 2 + la), 256);
       CKL();
     }

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(GPC_PD_NT, 1) k_potrf_diag(double* __restrict_
 // both 64-column halves before it stores either (its rows are read by no other CTA).
 // grid = 2 (nb - p - 1) - row0/64 ...: rows [r_lo, r_hi) in units of 64.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(gpc64::NT, 4) k_trsm_panel(double* __restrict__ A, const double* __restrict__ X,
+__global__ void __launch_bounds__(gpc64::NT, 2) k_trsm_panel(double* __restrict__ A, const double* __restrict__ X,
                                                              long ld, int p, int r64_lo) {
   extern __shared__ double sm[];
   const long r0 = ((long)r64_lo + blockIdx.x) * 64;
@@ -263,23 +263,26 @@ __global__ void __launch_bounds__(gpc64::NT, 4) k_trsm_panel(double* __restrict_
   double acc0[4][4][2], acc1[4][4][2];
   gpcg::zero_acc(acc0);
   gpcg::zero_acc(acc1);
-  gpc64::mainloop<false>(Arow, ld, Xpp, ld, 0, 64, acc0, sm);             // X_pp lower: columns 0..63 need k < 64
-  gpc64::mainloop<false>(Arow, ld, Xpp + 64 * ld, ld, 0, 128, acc1, sm);
+  // four-stage ring: the panel solve sits on the serial chain of the factorisation with far fewer CTAs than SMs
+  gpc64::mainloop<false, 4>(Arow, ld, Xpp, ld, 0, 64, acc0, sm);          // X_pp lower: columns 0..63 need k < 64
+  gpc64::mainloop<false, 4>(Arow, ld, Xpp + 64 * ld, ld, 0, 128, acc1, sm);
   gpc64::store_tile(Arow, ld, acc0, 1.0, 0.0);
   gpc64::store_tile(Arow + 64, ld, acc1, 1.0, 0.0);
 }
 
 // Trailing update: A_ij -= L_i,[p..] L_j,[p..]^T (kdim = 128: panel p, 256: panels p and p+1) over 64 x 64 tiles with row tile ti in [t_lo, t_hi) and column
 // tile tj in [c_lo, c_hi), tj <= ti (all in units of 64 rows).  grid (c_hi - c_lo, t_hi - t_lo).
-__global__ void __launch_bounds__(gpc64::NT, 4) k_syrk_panel(double* __restrict__ A, long ld, int p, int t_lo,
-                                                             int c_lo, int kdim) {
+// DEEP = the four-stage ring (80 KB) for the narrow look-ahead launches on the serial chain.
+template <bool DEEP>
+__global__ void __launch_bounds__(gpc64::NT, DEEP ? 2 : 4) k_syrk_panel(double* __restrict__ A, long ld, int p, int t_lo,
+                                                                        int c_lo, int kdim) {
   extern __shared__ double sm[];
   const int tj = c_lo + blockIdx.x, ti = t_lo + blockIdx.y;
   if (tj > ti) return;
   double acc[4][4][2];
   gpcg::zero_acc(acc);
-  gpc64::mainloop<false>(A + (long)ti * 64 * ld + (long)p * 128, ld, A + (long)tj * 64 * ld + (long)p * 128, ld, 0, kdim,
-                         acc, sm);
+  gpc64::mainloop<false, DEEP ? 4 : 2>(A + (long)ti * 64 * ld + (long)p * 128, ld, A + (long)tj * 64 * ld + (long)p * 128, ld,
+                                       0, kdim, acc, sm);
   gpc64::store_tile(A + (long)ti * 64 * ld + (long)tj * 64, ld, acc, -1.0, 1.0);
 }
 

@@ -169,6 +169,7 @@ constexpr int LDT = 20, LDN = 68;
 constexpr int A_STAGE = BM * LDT;                 // 1280 doubles
 constexpr int STAGE = A_STAGE + BN * LDT;         // B slot holds 64 x 20 (k-contiguous) or 16 x 68 (n-contiguous)
 constexpr int SMEM_BYTES = 2 * STAGE * 8;         // 40960
+constexpr int SMEM_BYTES_DEEP = 4 * STAGE * 8;    // 81920: the four-stage ring of the latency-critical launches
 
 template <bool B_N>
 __device__ __forceinline__ void load_stage(double* As, double* Bs, const double* __restrict__ A, long lda,
@@ -196,23 +197,29 @@ __device__ __forceinline__ void load_stage(double* As, double* Bs, const double*
 // acc += A[:, kbeg:kend] * op(B)[kbeg:kend, :]; kbeg / kend multiples of 16.  A: first row of the
 // 64-row tile (k contiguous).  B (B_N = false): first row of the 64-row tile (k contiguous);
 // B (B_N = true): column n0 of row k = 0 (rows are k).  On return the CTA is synchronised.
-template <bool B_N>
+// NS = ring depth: 2 (40 KB, 4 CTAs per SM) for the throughput-bound launches that fill the GPU; 4 (80 KB) for the
+// small launches on the critical path of the factorisation (a panel solve is 30 CTAs on 148 SMs: nothing else on
+// the SM covers the load latency, so three k-steps are kept in flight instead of one).
+template <bool B_N, int NS = 2>
 __device__ __forceinline__ void mainloop(const double* __restrict__ A, long lda, const double* __restrict__ B,
                                          long ldb, int kbeg, int kend, double (&acc)[4][4][2], double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1, lr = lane >> 2, lc = lane & 3;
   const int nk = (kend - kbeg) / BK;
-  if (nk > 0) load_stage<B_N>(smem, smem + A_STAGE, A, lda, B, ldb, kbeg, tid);
-  cp_async_commit();
+#pragma unroll
+  for (int s = 0; s < NS - 1; ++s) {
+    if (s < nk) load_stage<B_N>(smem + s * STAGE, smem + s * STAGE + A_STAGE, A, lda, B, ldb, kbeg + s * BK, tid);
+    cp_async_commit();
+  }
   for (int it = 0; it < nk; ++it) {
-    cp_async_wait<0>();
+    cp_async_wait<NS - 2>();
     __syncthreads();
-    if (it + 1 < nk) {
-      double* st = smem + ((it + 1) & 1) * STAGE;
-      load_stage<B_N>(st, st + A_STAGE, A, lda, B, ldb, kbeg + (it + 1) * BK, tid);
+    if (it + NS - 1 < nk) {
+      double* st = smem + ((it + NS - 1) % NS) * STAGE;
+      load_stage<B_N>(st, st + A_STAGE, A, lda, B, ldb, kbeg + (it + NS - 1) * BK, tid);
     }
     cp_async_commit();
-    const double* As = smem + (it & 1) * STAGE;
+    const double* As = smem + (it % NS) * STAGE;
     const double* Ap = As + (wm * 32 + lr) * LDT + lc;
     const double* Bp = B_N ? (As + A_STAGE + lc * LDN + wn * 32 + lr) : (As + A_STAGE + (wn * 32 + lr) * LDT + lc);
 #pragma unroll

@@ -177,6 +177,10 @@ int set_gemm_attrs(gpc_handle h) {
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_SUMSQ, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_F64, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_vt_i8<OUT_DIGITS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gpoz::SMEM_BYTES));
@@ -464,7 +468,7 @@ double v_scale(gpc_handle h) {
 }
 
 // Digit levels of the INT8 contraction: 6 (21 digit GEMMs, FP64 results) or 4 in the FP32-tolerance mode (10 GEMMs).
-inline int i8_levels(gpc_handle h) { return h->mode == GPC_MODE_INT8_F32 ? 4 : gpoz::S; }
+inline int i8_levels(gpc_handle h) { return h->mode == GPC_MODE_INT8_F32 ? 4 : (h->mode == GPC_MODE_INT8_L5 ? 5 : gpoz::S); }
 
 template <int OUT, bool FULLK>
 int launch_i8(gpc_handle h, const VtI8Args& a, double fp64_equiv_flops) {
@@ -483,6 +487,7 @@ int launch_i8(gpc_handle h, const VtI8Args& a, double fp64_equiv_flops) {
     CK(cudaEventRecord(e0, h->stream));
   }
   if (a.nlev == gpoz::S) k_vt_i8<OUT, FULLK, gpoz::S><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
+  else if (a.nlev == 5) k_vt_i8<OUT, FULLK, 5><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
   else k_vt_i8<OUT, FULLK, 4><<<grid, gpoz::NT, gpoz::SMEM_BYTES, h->stream>>>(a);
   CKL();
   if (h->hot_timing) {
@@ -1493,7 +1498,8 @@ long gpc_launch_count(gpc_handle h) { return h ? h->launches : 0; }
 
 int gpc_set_mode(gpc_handle h, int mode) {
   if (!h) return GPC_ERR_ARG;
-  if (mode != GPC_MODE_FP64 && mode != GPC_MODE_INT8 && mode != GPC_MODE_INT8_F32) return fail(h, GPC_ERR_ARG, "unknown mode");
+  if (mode != GPC_MODE_FP64 && mode != GPC_MODE_INT8 && mode != GPC_MODE_INT8_F32 && mode != GPC_MODE_INT8_L5)
+    return fail(h, GPC_ERR_ARG, "unknown mode");
   h->mode = mode;
   return GPC_OK;
 }

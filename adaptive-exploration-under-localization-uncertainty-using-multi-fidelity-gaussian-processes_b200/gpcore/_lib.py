@@ -19,7 +19,7 @@ GPC_OK, GPC_ERR_NOT_PD, GPC_ERR_SHAPE, GPC_ERR_CUDA, GPC_ERR_STATE, GPC_ERR_ARG 
 KIND_SF_RBF, KIND_SF_MAT32, KIND_MF_AR1_RBF, KIND_MF_AR1_MAT32, KIND_NIGP = range(5)
 INCLUDE_NOISE, CLIP_DIAG, CLIP_COV, NIGP_FLOOR, MEAN_ONLY = 1, 2, 4, 8, 16
 IG_FIRST_PREADDED = 1
-MODE_FP64, MODE_INT8, MODE_INT8_F32 = 0, 1, 2
+MODE_FP64, MODE_INT8, MODE_INT8_F32, MODE_INT8_L5 = 0, 1, 2, 3
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -621,7 +621,28 @@ def run_ours(args):
             other["int8_f32_tolerance_mode"] = {"value": M * 3 / (fms * 1e-3), "ms_per_step": fms / 3,
                                                 "note": "GPC_MODE_INT8_F32: variances to ~1e-7 relative (north_star allows 1e-4 "
                                                         "for an optional FP32 mode); NOT the headline metric"}
+            # five of the six digit levels (15 digit GEMMs): the error-budgeted variant VERDICT r1 asked to evaluate.
+            # Timed AND checked against the oracle here; not the default because its margin to 1e-9 is a factor of two
+            core.set_mode(L.MODE_INT8_L5)
+            for _ in range(2):
+                step_dev()
+            torch.cuda.synchronize()
+            lms = timed(step_dev, 3, 0)
+            l5 = {"value": M * 3 / (lms * 1e-3), "ms_per_step": lms / 3}
+            if args.parity and not nigp_mode:
+                from oracle import gp_oracle as go
+                idx = np.unique(np.linspace(0, M - 1, 4096).astype(np.int64))
+                refp = go.MFGP(X4, y, MF2_PARAMS, F=2, gram=False)
+                _, vr = refp.predict(np.ascontiguousarray(Xs4_host[idx]))
+                dv5 = dvar.cpu().numpy()[idx]
+                sc5 = float(MF2_PARAMS[0] * MF2_PARAMS[8] ** 2 + MF2_PARAMS[4])
+                l5["max_rel_var"] = float(np.max(np.abs(dv5 - vr[:, 0])) / max(float(np.max(vr)), sc5))
+                l5["max_elem_rel_var"] = float(np.max(np.abs(dv5 - vr[:, 0]) / vr[:, 0]))
+            l5["note"] = "GPC_MODE_INT8_L5: opt-in; normwise margin to 1e-9 is ~2x, information gain is outside 1e-9 in this mode"
+            other["int8_five_levels"] = l5
             core.set_mode(mode)
+            step_dev()               # leave the default mode's results in the output buffers
+            torch.cuda.synchronize()
         except Exception as exc:   # context only
             other = {"error": str(exc)}
 

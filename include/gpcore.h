@@ -70,6 +70,11 @@ enum gpc_kind {
  *                  relative -- three orders inside an FP32 evaluation of the same cancellation-prone difference --
  *                  at about half the contraction time.  The mean is unaffected (it is formed in FP64 either way). */
 #define GPC_MODE_INT8_F32 2
+/*   GPC_MODE_INT8_L5   five of the six digit levels (15 digit GEMMs, -29 % tensor work): posterior variances to ~5e-10
+ *                  normwise at the BASELINE sizes -- inside the 1e-9 tolerance by a factor of two only, which is why it
+ *                  is NOT the default -- and information gain outside 1e-9 (~3e-8).  An explicit speed / margin
+ *                  trade for callers that only need the posterior. */
+#define GPC_MODE_INT8_L5 3
 
 /* gpc_ig_seq flags */
 #define GPC_IG_FIRST_PREADDED 1u /* GraceRIGV3.py:454-455: point 0 is appended before it is predicted */

@@ -246,3 +246,49 @@ def test_fp32_tolerance_mode(gpcore_mod, go):
     m2, v2 = core.predict(Xs4, flags)
     assert normwise(v2, var[:, 0], 4.64) < TOL
     core.close()
+
+
+def test_host_predict_stages_with_per_row_input_noise(gpcore_mod):
+    """NIGP.predict with a per-row Xs_input_noise (M, D) array on more rows than one device stage (2^17): the noise
+    rows travel through the same pinned staging ring as the test rows.  A 300 001-row call must equal the same rows
+    predicted in independent single-stage calls."""
+    from gpcore.nigp import NIGP
+    g, d = golden("nigp_field.npz"), golden("field_data.npz")
+    m = NIGP(verbose=False)
+    m.lengthscales_, m.sigma_f_, m.sigma_y_, m.sigma_x_ = g["ls"], float(g["sigma_f"]), float(g["sigma_y"]), g["sigma_x"]
+    m.X_train_, m.y_train_, m.noise_diag_train_ = d["Xh"], d["y"], g["noise_diag"]
+    rng = np.random.default_rng(12)
+    M = 300001
+    Xs = rng.uniform([0, 0, 0], [10, 20, 10], (M, 3))
+    sx = rng.uniform(0.01, 0.3, (M, 3))
+    mean, var = m.predict(Xs, Xs_input_noise=sx)
+    assert np.all(np.isfinite(mean)) and np.all(var >= 1e-12)
+    for lo in (0, 131000, 262000, 299000):
+        hi = min(M, lo + 1101)
+        m0, v0 = m.predict(np.ascontiguousarray(Xs[lo:hi]), Xs_input_noise=np.ascontiguousarray(sx[lo:hi]))
+        assert np.array_equal(mean[lo:hi], m0) and np.array_equal(var[lo:hi], v0), lo
+    # one shared (D,) noise vector gives the same as its tiled (M, D) form
+    _, v1 = m.predict(Xs[:5000], Xs_input_noise=g["sigma_x"])
+    _, v2 = m.predict(Xs[:5000], Xs_input_noise=np.tile(g["sigma_x"], (5000, 1)))
+    assert np.allclose(v1, v2, rtol=1e-13, atol=0)
+
+
+def test_five_level_mode_is_inside_the_normwise_tolerance_only(gpcore_mod):
+    """GPC_MODE_INT8_L5 (15 of the 21 digit GEMMs): an opt-in speed / margin trade.  At configs[1]'s size its posterior
+    variance stays inside the 1e-9 NORMWISE tolerance (measured ~5e-10) but not element-wise, which is why the default
+    keeps all six levels."""
+    import scale_cases as sc
+    L_ = gpcore_mod._lib
+    X4, y, p, Xs4 = sc.configs1_inputs()
+    o, _ = sc.frozen_or_live("c1", sc.configs1_oracle, sc.sha(X4, y, p, Xs4))
+    core = gpcore_mod.GPCore(L_.KIND_MF_AR1_RBF, 2, 0)
+    core.set_hypers(p, 1e-8)
+    core.set_data(X4, y)
+    core.factor()
+    core.set_mode(L_.MODE_INT8_L5)
+    m1, v1 = core.predict(Xs4, L_.INCLUDE_NOISE | L_.CLIP_DIAG)
+    scale = float(p[0] * p[8] ** 2 + p[4])
+    nm, nv = normwise(m1, o["c1_mu"]), normwise(v1, o["c1_var"], scale)
+    print("INT8_L5: normwise mean %.2e var %.2e, element-wise var %.2e" % (nm, nv, np.max(np.abs(v1 - o["c1_var"]) / o["c1_var"])))
+    assert nm < TOL and nv < TOL
+    core.close()

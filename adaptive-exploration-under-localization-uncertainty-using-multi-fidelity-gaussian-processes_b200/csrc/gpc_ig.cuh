@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256, 2) k_ig_logdet_clip(const __grid_constant
   const int sdim = (kcap * GPC_IG_LD > 2 * NB * LDD) ? kcap * GPC_IG_LD : 2 * NB * LDD;
   double* S = dsm;                 // candidate covariance, dead once W^T exists ...
   double* D = dsm;                 // ... then the diagonal block and the staged multipliers live there
-  double* Lp = D + NB * LDD;
+  double* Lp = D + NB * LDD;       // [32][32], no padding: its reads are warp-wide broadcasts, 16-byte vectorisable
   double(*pt)[4] = reinterpret_cast<double(*)[4]>(dsm + sdim);
   double* red = dsm + sdim + kcap * 4;
   int* flagp = reinterpret_cast<int*>(red + 16);
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256, 2) k_ig_logdet_clip(const __grid_constant
         }
         for (int j0 = 0; j0 < p0; j0 += NB) {
           __syncthreads();
-          for (int e = tid; e < NB * NB; e += blockDim.x) Lp[(e >> 5) * LDD + (e & 31)] = Lt[(size_t)(j0 + (e >> 5)) * GP + p0 + (e & 31)];
+          for (int e = tid; e < NB * NB; e += blockDim.x) Lp[e] = Lt[(size_t)(j0 + (e >> 5)) * GP + p0 + (e & 31)];
           __syncthreads();
           if (act) {
             // the multipliers of this row come out of the L2-resident scratch: fetch eight at a time so that
@@ -476,37 +476,46 @@ __global__ void __launch_bounds__(256, 2) k_ig_logdet_clip(const __grid_constant
               for (int u = 0; u < 8; ++u) av[u] = Lt[(size_t)(j0 + j8 + u) * GP + i];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
+                const double2* lp2 = reinterpret_cast<const double2*>(Lp + (j8 + u) * NB);
 #pragma unroll
-                for (int cc = 0; cc < NB; ++cc) acc[cc] = fma(-av[u], Lp[(j8 + u) * LDD + cc], acc[cc]);
+                for (int cc = 0; cc < NB; cc += 2) {
+                  const double2 l2 = lp2[cc >> 1];
+                  acc[cc] = fma(-av[u], l2.x, acc[cc]);
+                  acc[cc + 1] = fma(-av[u], l2.y, acc[cc + 1]);
+                }
               }
             }
           }
         }
-        if (base == p0) {   // the 32 rows of the diagonal block are threads 0..31 of this chunk
-          __syncthreads();
-          if (tid < NB) {
-#pragma unroll
-            for (int cc = 0; cc < NB; ++cc) D[tid * LDD + cc] = acc[cc];
-          }
-          __syncthreads();
+        if (base == p0) {   // the 32 rows of the diagonal block are threads 0..31 (warp 0) of this chunk
+          // acc[] of lane l IS row l of the diagonal block: factor it in place, in registers.  Per column the pivot
+          // travels by one shuffle, every lane takes its reciprocal square root itself, and the multipliers
+          // L[l2][j] come by one shuffle each (the scheme of k_potrf_diag's 16 x 16 block; the shared-memory version
+          // with sqrt, divide and a per-lane update loop cost ~25 us per block, a third of the kernel).
+          __syncthreads();                                    // every reader of the previous D / rdiag is done
           if (tid < NB) {
             const int lane = tid;
+            double mydiag = 1.0;
+#pragma unroll
             for (int j = 0; j < NB; ++j) {
-              const double d = D[j * LDD + j];
-              if (!(d > 0.0)) bad = 1;
-              const double sq = sqrt(d);
-              __syncwarp();
-              if (lane == j) D[j * LDD + j] = sq;
-              if (lane > j) D[lane * LDD + j] /= sq;
-              __syncwarp();
-              if (lane > j) {
-                const double a = D[lane * LDD + j];
-                for (int l = j + 1; l <= lane; ++l) D[lane * LDD + l] = fma(-a, D[l * LDD + j], D[lane * LDD + l]);
+              double d = __shfl_sync(0xffffffffu, acc[j], j);
+              if (!(d > 0.0)) {
+                bad = 1;
+                d = 1.0;
               }
-              __syncwarp();
+              const double inv = rsqrt(d);
+              acc[j] *= inv;                                  // L[lane][j] (unused for lane < j)
+              if (lane == j) mydiag = d * inv;                // sqrt(d)
+#pragma unroll
+              for (int l2 = j + 1; l2 < NB; ++l2) {
+                const double cj = __shfl_sync(0xffffffffu, acc[j], l2);   // L[l2][j]
+                acc[l2] = fma(-acc[j], cj, acc[l2]);
+              }
             }
-            ldsum += log(D[lane * LDD + lane]);
-            rdiag[lane] = 1.0 / D[lane * LDD + lane];
+            ldsum += log(mydiag);
+            rdiag[lane] = 1.0 / mydiag;
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) D[lane * LDD + cc] = acc[cc];   // entries right of the diagonal are never read
           }
           __syncthreads();
         }

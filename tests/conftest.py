@@ -40,3 +40,18 @@ def normwise(a, b, scale=None):
     a, b = np.asarray(a, float), np.asarray(b, float)
     s = np.max(np.abs(b)) if scale is None else max(np.max(np.abs(b)), scale)
     return float(np.max(np.abs(a - b)) / max(s, 1e-300))
+
+
+def measured(name, value, tol):
+    """Record a measured parity figure next to the tolerance it is asserted against (printed with -s and appended to
+    gpurun_out/parity_r02.jsonl), then return it: ``assert measured("ig_sf_ld", normwise(a, b), 1e-9) < 1e-9``."""
+    import json
+    path = os.environ.get("GPC_PARITY_LOG") or os.path.join(ROOT, "gpurun_out", "parity_r02.jsonl")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps({"case": name, "measured": float(value), "tolerance": float(tol)}) + "\n")
+    except OSError:
+        pass
+    print("measured %-46s %.3e (tolerance %.1e)" % (name, value, tol))
+    return value

@@ -6,18 +6,20 @@ max|gpu - ref| <= 1e-9 * max(|ref|, kernel variance) -- because var = k** - |L^-
 (SURVEY.md section 7).  Reference values come from (a) the reference's own NIGP.py
 (tests/golden/nigp_*.npz, pinned) and (b) the NumPy restatement of the GPy/emukit arithmetic
 (unpinned third-party boundary), evaluated with direct distances (`gram=False`, the same
-formulation the kernels use) at 1e-9 and with GPy's Gram-trick distances (`gram=True`) at the
-looser GRAM_TOL, which is the spread between the two CPU formulations themselves.
+formulation the kernels use) and with GPy's Gram-trick distances (`gram=True`, the frozen golden arrays), both at
+1e-9: every assert of this file and of tests/test_gpu_int8.py that round 1 had loosened to 1e-8 .. 1e-7 now holds the
+north star's 1e-9 (measured values are printed by `measured()` and logged; the worst is 7e-10, an FP64 mean at
+cond(K) ~ 1e7).
 """
 import numpy as np
 import pytest
 
-from conftest import golden, normwise
+from conftest import golden, measured, normwise
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-9
-GRAM_TOL = 2e-8
+GRAM_TOL = TOL     # round 1 allowed 2e-8 against the Gram-trick goldens; the measured spread is <= 4e-11
 
 
 @pytest.fixture(scope="module")
@@ -248,7 +250,8 @@ def test_sfgp_predict_field(gpcore_mod, go, kind):
     mu0, var0 = ref.predict(d["test"])
     assert normwise(mu, mu0) < TOL and normwise(var, var0, 4.0) < TOL
     gmu, gvar = (g["mu_sf"], g["var_sf"]) if kind == "rbf" else (g["mu_32"], g["var_32"])
-    assert normwise(mu, gmu) < GRAM_TOL and normwise(var, gvar, 4.0) < GRAM_TOL   # Gram-trick CPU formulation
+    assert measured("sf_vs_gram_golden_mean_" + kind, normwise(mu, gmu), GRAM_TOL) < GRAM_TOL   # Gram-trick CPU formulation
+    assert measured("sf_vs_gram_golden_var_" + kind, normwise(var, gvar, 4.0), GRAM_TOL) < GRAM_TOL
     assert abs(gp.objective_function() - ref.f.nlml) < TOL * abs(ref.f.nlml)
     mu2, cov = gp.predict(d["test_sub"], full_cov=1)
     _, cov0 = ref.predict(d["test_sub"], full_cov=True)
@@ -319,10 +322,12 @@ def test_mfgp_predict_field(gpcore_mod, go, noise_mode):
     assert normwise(cov, ref.predict_covariance(s4), scale) < TOL
     assert cov.min() >= 1e-10                                 # emukit's element-wise clip
     if noise_mode == "mixed":
-        assert normwise(mu, g["mu_mf"]) < GRAM_TOL and normwise(var, g["var_mf"], scale) < GRAM_TOL
+        assert measured("mf_vs_gram_golden_mean", normwise(mu, g["mu_mf"]), GRAM_TOL) < GRAM_TOL
+        assert measured("mf_vs_gram_golden_var", normwise(var, g["var_mf"], scale), GRAM_TOL) < GRAM_TOL
         lo4 = np.hstack([d["test_sub"], np.zeros((250, 1))])
         a, b = w.predict(lo4)                                 # lowest fidelity: only k_0 and noise_0
-        assert normwise(a, g["mu_mf0"]) < GRAM_TOL and normwise(b, g["var_mf0"], scale) < GRAM_TOL
+        assert measured("mf0_vs_gram_golden_mean", normwise(a, g["mu_mf0"]), GRAM_TOL) < GRAM_TOL
+        assert measured("mf0_vs_gram_golden_var", normwise(b, g["var_mf0"], scale), GRAM_TOL) < GRAM_TOL
     Kxx = m.kern.K(s4)
     v, ls, rho, _ = go.split_mf_params(params, 3)
     assert normwise(Kxx, go.k_ar1(s4, s4, v, ls, rho, gram=False, same=True)) < 1e-13
@@ -425,7 +430,7 @@ def test_ig_sequential_sf_golden(gpcore_mod, go):
     gp.param_array[:] = SF_PARAMS
     cands = [c[:, :3] for c in _cands_from_golden(g)]
     I, best = seq_info_gain(gp, cands, SF_PARAMS[-1], first_preadded=True)
-    assert normwise(I, g["ig_sf_seq"]) < GRAM_TOL                 # literal refit loop, Gram-trick CPU
+    assert measured("ig_sf_seq_vs_gram_golden", normwise(I, g["ig_sf_seq"]), GRAM_TOL) < GRAM_TOL   # literal refit loop, Gram-trick CPU
     ref = go.SFGP(d["Xh"], d["y"], SF_PARAMS, gram=False)
     I0 = np.array([go.ig_seq_sf_refit(ref, c, first_preadded=True) for c in cands[:4]])
     assert normwise(I[:4], I0) < TOL
@@ -443,7 +448,7 @@ def test_ig_sequential_mf_golden(gpcore_mod, go):
     core.set_data(g["X4"], g["y4"])
     core.factor()
     I, best = core.ig_seq(g["cand_rows"], g["cand_off"], MF_PARAMS[-1], pred_fid=0)
-    assert normwise(I, g["ig_mf_seq"]) < GRAM_TOL
+    assert measured("ig_mf_seq_vs_gram_golden", normwise(I, g["ig_mf_seq"]), GRAM_TOL) < GRAM_TOL
     ref = go.MFGP(g["X4"], g["y4"], MF_PARAMS, F=3, gram=False)
     cands = _cands_from_golden(g)
     I0 = np.array([go.ig_seq_mf_refit(ref, c, MF_PARAMS[-1], 0) for c in cands[:4]])
@@ -469,12 +474,12 @@ def test_ig_logdet_golden(gpcore_mod, go):
     grid4 = np.hstack([d["ig_grid"], np.zeros((len(d["ig_grid"]), 1))])
     rows = g["cand_rows"].copy(); rows[:, 3] = 0
     I, prior, best = core.ig_logdet(grid4, rows, g["cand_off"])
-    assert normwise(I, g["ig_sf_ld"], 1.0) < 1e-7             # G = 300 log-dets of a refit: looser CPU-side conditioning
+    assert measured("ig_sf_logdet_vs_gram_golden", normwise(I, g["ig_sf_ld"], 1.0), TOL) < TOL   # G = 300 log-dets of a Gram-trick refit
     ref = go.SFGP(d["Xh"], d["y"], SF_PARAMS, gram=False)
     I0 = np.array([go.ig_logdet_refit(ref, d["ig_grid"], c[:, :3]) for c in cands[:3]])
-    assert normwise(I[:3], I0, 1.0) < 1e-8
+    assert measured("ig_sf_logdet_vs_refit", normwise(I[:3], I0, 1.0), TOL) < TOL
     _, cov = ref.predict(d["ig_grid"], full_cov=True)
-    assert abs(prior - np.linalg.slogdet(cov)[1]) < 1e-8 * abs(prior)
+    assert measured("ig_sf_logdet_prior", abs(prior - np.linalg.slogdet(cov)[1]) / abs(prior), TOL) < TOL
     assert best == int(np.argmax(g["ig_sf_ld"]))
     core.close()
     # multi fidelity, grid at fidelity 2
@@ -484,7 +489,7 @@ def test_ig_logdet_golden(gpcore_mod, go):
     core.factor()
     g4 = np.hstack([d["ig_grid"], 2 * np.ones((len(d["ig_grid"]), 1))])
     I, prior, best = core.ig_logdet(g4, g["cand_rows"], g["cand_off"])
-    assert normwise(I, g["ig_mf_ld"], 1.0) < 1e-7
+    assert measured("ig_mf_logdet_vs_gram_golden", normwise(I, g["ig_mf_ld"], 1.0), TOL) < TOL
     assert best == int(np.argmax(g["ig_mf_ld"]))
     core.close()
 
@@ -579,7 +584,7 @@ def test_ig_agent_operators(gpcore_mod, go):
     ag.logDetPrior = None
     J = ag.calcPathInfoSFBatch_many(None, E, paths)
     wantJ = np.array([max(go.ig_logdet_refit(refsf, d["ig_grid"], E[c][1:, :3]), 0) for c in paths])
-    assert normwise(J, wantJ, 1.0) < 1e-8 and ag.logDetPrior is not None
+    assert measured("agent_sfbatch_vs_refit", normwise(J, wantJ, 1.0), TOL) < TOL and ag.logDetPrior is not None
     # log-det MF (calculatePathInfoEmuBatch), fidelity labels from the variance column
     from gpcore.infogain import label_fidelity
     ag.logDetPrior = None
@@ -588,7 +593,7 @@ def test_ig_agent_operators(gpcore_mod, go):
     wantJm = np.array([go.ig_logdet_refit(refmf, g4, np.hstack([E[c][:, :3], label_fidelity(E[c][:, 4], ag.fidLevs)[:, None]]),
                                           clip_cov=1e-10)      # emukit predict_covariance clips element-wise
                        for c in paths])
-    assert normwise(Jm, wantJm, 1.0) < 1e-8
+    assert measured("agent_emubatch_clip_vs_refit", normwise(Jm, wantJm, 1.0), TOL) < TOL
     # sequential MF, un-windowed core (calculatePathInfoEmu with the window switched off)
     Is = ag.calculatePathInfoEmu_many(None, E, paths, windowed=False)
     wantIs = np.array([go.ig_seq_mf_refit(refmf, np.hstack([E[c][:, :3], label_fidelity(E[c][:, 4], ag.fidLevs)[:, None]]),
@@ -606,7 +611,7 @@ def test_ig_agent_operators(gpcore_mod, go):
             tmp = go.MFGP(tempX, np.zeros(len(tempX)), MF_PARAMS, F=3, gram=False)
             q = X[i:i + 1].copy(); q[0, 3] = 0
             tot += np.log(1 + tmp.predict(q)[1][0, 0] / MF_PARAMS[-1])
-        assert abs(Iw[ci] - tot) < 1e-8 * abs(tot), (ci, Iw[ci], tot)
+        assert measured("agent_emu_windowed_vs_loop_%d" % ci, abs(Iw[ci] - tot) / abs(tot), TOL) < TOL, (ci, Iw[ci], tot)
     # reference quirk (PhysicalExperimentCode/GraceRIGV3.py:608-611): the single-path operator scores on a cached copy
     # mfgp2 whose DATA follow the agent but whose HYPER-PARAMETERS stay those of the moment the copy was made
     ag.logDetPrior = None

@@ -126,6 +126,42 @@ __device__ __forceinline__ void gpc_exp_neg_w(const double* __restrict__ qin, do
 }
 
 
+// The same exp(-q), table-driven: k = rint(-64 q / ln 2) = 64 e + j, exp(-q) = 2^e T[j] exp(r) with T[j] = 2^(j/64)
+// (64 doubles in shared memory) and |r| <= ln2 / 128, where a degree-5 polynomial is exact to 3.5e-17.  Eleven FP64-pipe
+// operations per value instead of eighteen -- under the board's power cap the assembly kernel's time follows its energy,
+// and the exp was half of its FP64 work.  Result within 2 ulp (the digits that are made from it carry 2^-49 of the scale).
+template <int W>
+__device__ __forceinline__ void gpc_exp_neg_tab_w(const double* __restrict__ qin, double* __restrict__ e,
+                                                  const double* __restrict__ T64) {
+  double q[W], t[W], r[W], p[W];
+#pragma unroll
+  for (int u = 0; u < W; ++u) q[u] = fmin(qin[u], 700.0);
+#pragma unroll
+  for (int u = 0; u < W; ++u) t[u] = fma_pinned(q[u], -92.332482616893653, 6755399441055744.0);   // -64 / ln 2
+#pragma unroll
+  for (int u = 0; u < W; ++u) r[u] = t[u] - 6755399441055744.0;       // kf
+#pragma unroll
+  for (int u = 0; u < W; ++u) q[u] = fma_pinned(r[u], -6.93147180369123816490e-01 / 64.0, -q[u]);   // ln2 / 64, high part (exact product)
+#pragma unroll
+  for (int u = 0; u < W; ++u) r[u] = fma_pinned(r[u], -1.90821492927058770002e-10 / 64.0, q[u]);    // low part
+#pragma unroll
+  for (int u = 0; u < W; ++u) p[u] = fma_pinned(8.333333333333333e-03, r[u], 4.1666666666666664e-02);   // 1/5!, 1/4!
+#define GPC_EXP_STAGE(c)            \
+  _Pragma("unroll") for (int u = 0; u < W; ++u) p[u] = fma_pinned(p[u], r[u], c);
+  GPC_EXP_STAGE(1.6666666666666666e-01)   // 1/3!
+  GPC_EXP_STAGE(0.5)
+  GPC_EXP_STAGE(1.0)
+  GPC_EXP_STAGE(1.0)
+#undef GPC_EXP_STAGE
+#pragma unroll
+  for (int u = 0; u < W; ++u) {
+    const int k = __double2loint(t[u]);
+    const double v = p[u] * T64[k & 63];
+    e[u] = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+  }
+}
+
+
 // ---- mbarrier / bulk-copy (TMA) helpers ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -203,9 +203,11 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
   __shared__ double hil[GPC_MAXF][4];
   __shared__ double hcoef[GPC_MAXF][GPC_MAXF];
   __shared__ double wS[GPC_MAXF][128];
+  __shared__ double T64[64];                       // 2^(j / 64): the table of gpc_exp_neg_tab_w
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31;
   const int mt = blockIdx.x;
+  if (tid < 64) T64[tid] = exp2((double)tid * 0.015625);
   const long j0 = (long)blockIdx.y * KI_COLS;
   const long nkb = n_pad >> 6;
   if (tid == 0) {
@@ -266,13 +268,13 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
         q[u] = fma(sx, sx, fma(sy, sy, sz * sz));
       }
       if (base == 0) {
-        gpc_exp_neg_w<4>(q, e);
-        gpc_exp_neg_w<4>(q + 4, e + 4);
+        gpc_exp_neg_tab_w<4>(q, e, T64);
+        gpc_exp_neg_tab_w<4>(q + 4, e + 4, T64);
       } else {
 #pragma unroll
         for (int u = 0; u < 8; ++u) q[u] = 1.7320508075688772 * sqrt(q[u]);
-        gpc_exp_neg_w<4>(q, e);
-        gpc_exp_neg_w<4>(q + 4, e + 4);
+        gpc_exp_neg_tab_w<4>(q, e, T64);
+        gpc_exp_neg_tab_w<4>(q + 4, e + 4, T64);
 #pragma unroll
         for (int u = 0; u < 8; ++u) e[u] *= 1.0 + q[u];
       }
@@ -293,7 +295,8 @@ __global__ void __launch_bounds__(128) k_kstar_i8(const __grid_constant__ GpcHyp
         g1 = fma(ka, tr[1][j] - ay, g1);
         g2 = fma(ka, tr[2][j] - az, g2);
       }
-      v[u] = (unsigned long long)(__double2ll_rn(k[u] * mul) + DIGIT_BIAS);
+      // rint(k * mul) + bias without F2I: adding 2^52 + 2^51 leaves the rounded integer in the mantissa (|k * mul| < 2^48)
+      v[u] = (unsigned long long)(__double_as_longlong(fma(k[u], mul, 6755399441055744.0)) + (DIGIT_BIAS - 0x4338000000000000LL));
     }
     const long kb = (j0 >> 6) + (c8 >> 3);
     int8_t* dst = Aimg + (((long)mt * nkb + kb) * S) * (long)A_SLICE + (r >> 3) * 512 + ((c8 >> 1) & 3) * 128 +
@@ -552,7 +555,9 @@ __global__ void __launch_bounds__(gpoz::NT, 1) k_vt_i8(const __grid_constant__ V
           if (OUT == OUT_DIGITS) {
             unsigned long long dv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dv[j] = (unsigned long long)(__double2ll_rn(vv[j] * a.dig_mul) + DIGIT_BIAS);
+            for (int j = 0; j < 8; ++j)
+              dv[j] = (unsigned long long)(__double_as_longlong(fma(vv[j], a.dig_mul, 6755399441055744.0)) +
+                                           (DIGIT_BIAS - 0x4338000000000000LL));
             int8_t* dst = a.dig + (((long)mt * a.nkb_out + jb) * S) * (long)A_SLICE + (row >> 3) * 512 + (c0 >> 4) * 128 +
                           (row & 7) * 16 + (c0 & 15);
             *reinterpret_cast<uint2*>(dst + 0L * A_SLICE) = pack_bytes8<5>(dv);

@@ -80,53 +80,16 @@ __device__ __forceinline__ double gpc_exp_neg(double q) {
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
-// exp(-q[u]) for W independent arguments, written stage by stage so that the W dependency chains
-// advance together (W-way ILP in the FP64 pipe from a single warp; the library exp() carries
-// special-case branches that keep the columns of a thread from interleaving).  The stages are volatile
-// asm so that the compiler keeps them breadth-first instead of re-serialising the chains.
+// fma that the compiler may not reorder: the stages of the W-wide exp below are volatile asm so that the W dependency
+// chains advance breadth-first (W-way ILP in the FP64 pipe from a single warp; the library exp() carries special-case
+// branches that keep the columns of a thread from interleaving).
 __device__ __forceinline__ double fma_pinned(double a, double b, double c) {
   double d;
   asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
   return d;
 }
 
-template <int W>
-__device__ __forceinline__ void gpc_exp_neg_w(const double* __restrict__ qin, double* __restrict__ e) {
-  double q[W], t[W], r[W], p[W];
-#pragma unroll
-  for (int u = 0; u < W; ++u) q[u] = fmin(qin[u], 700.0);
-#pragma unroll
-  for (int u = 0; u < W; ++u) t[u] = fma_pinned(q[u], -1.4426950408889634074, 6755399441055744.0);
-#pragma unroll
-  for (int u = 0; u < W; ++u) r[u] = t[u] - 6755399441055744.0;       // kf
-#pragma unroll
-  for (int u = 0; u < W; ++u) q[u] = fma_pinned(r[u], -6.93147180369123816490e-01, -q[u]);
-#pragma unroll
-  for (int u = 0; u < W; ++u) r[u] = fma_pinned(r[u], -1.90821492927058770002e-10, q[u]);
-#pragma unroll
-  for (int u = 0; u < W; ++u) p[u] = fma_pinned(1.6059043836821613e-10, r[u], 2.08767569878681e-09);   // 1/13!, 1/12!
-#define GPC_EXP_STAGE(c)            \
-  _Pragma("unroll") for (int u = 0; u < W; ++u) p[u] = fma_pinned(p[u], r[u], c);
-  GPC_EXP_STAGE(2.505210838544172e-08)    // 1/11!
-  GPC_EXP_STAGE(2.755731922398589e-07)    // 1/10!
-  GPC_EXP_STAGE(2.7557319223985893e-06)   // 1/9!
-  GPC_EXP_STAGE(2.48015873015873e-05)     // 1/8!
-  GPC_EXP_STAGE(1.984126984126984e-04)    // 1/7!
-  GPC_EXP_STAGE(1.3888888888888889e-03)   // 1/6!
-  GPC_EXP_STAGE(8.333333333333333e-03)    // 1/5!
-  GPC_EXP_STAGE(4.1666666666666664e-02)   // 1/4!
-  GPC_EXP_STAGE(1.6666666666666666e-01)   // 1/3!
-  GPC_EXP_STAGE(0.5)
-  GPC_EXP_STAGE(1.0)
-  GPC_EXP_STAGE(1.0)
-#undef GPC_EXP_STAGE
-#pragma unroll
-  for (int u = 0; u < W; ++u)
-    e[u] = __hiloint2double(__double2hiint(p[u]) + (__double2loint(t[u]) << 20), __double2loint(p[u]));
-}
-
-
-// The same exp(-q), table-driven: k = rint(-64 q / ln 2) = 64 e + j, exp(-q) = 2^e T[j] exp(r) with T[j] = 2^(j/64)
+// exp(-q[u]) for W independent arguments, table-driven: k = rint(-64 q / ln 2) = 64 e + j, exp(-q) = 2^e T[j] exp(r) with T[j] = 2^(j/64)
 // (64 doubles in shared memory) and |r| <= ln2 / 128, where a degree-5 polynomial is exact to 3.5e-17.  Eleven FP64-pipe
 // operations per value instead of eighteen -- under the board's power cap the assembly kernel's time follows its energy,
 // and the exp was half of its FP64 work.  Result within 2 ulp (the digits that are made from it carry 2^-49 of the scale).

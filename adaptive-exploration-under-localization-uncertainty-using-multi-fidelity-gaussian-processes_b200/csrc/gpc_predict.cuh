@@ -36,8 +36,10 @@ __global__ void __launch_bounds__(256) k_kstar(const __grid_constant__ GpcHyp h,
   __shared__ double cw[8][GPC_MAXF][GPC_MAXF];   // per warp
   __shared__ double hil[GPC_MAXF][4];            // inv lengthscales (pre-scaled), shared copy of the hypers
   __shared__ int bmax[KS_COLS / 128];
+  __shared__ double T64[64];                     // 2^(j / 64): the table of gpc_exp_neg_tab_w
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 64) T64[tid] = exp2((double)tid * 0.015625);
   const long row0 = (long)blockIdx.x * KS_ROWS;
   const long j0 = (long)blockIdx.y * KS_COLS;
   const int ncol = (int)((n_pad - j0) < KS_COLS ? (n_pad - j0) : KS_COLS);  // multiple of 128
@@ -125,11 +127,11 @@ __global__ void __launch_bounds__(256) k_kstar(const __grid_constant__ GpcHyp h,
           q[u] = fma(sx, sx, fma(sy, sy, sz * sz));
         }
         if (base == 0) {
-          gpc_exp_neg_w<4>(q, e);      // branch-free, the four columns of the lane advance together
+          gpc_exp_neg_tab_w<4>(q, e, T64);      // branch-free, the four columns of the lane advance together
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u) q[u] = 1.7320508075688772 * sqrt(q[u]);
-          gpc_exp_neg_w<4>(q, e);
+          gpc_exp_neg_tab_w<4>(q, e, T64);
 #pragma unroll
           for (int u = 0; u < 4; ++u) e[u] *= 1.0 + q[u];
         }

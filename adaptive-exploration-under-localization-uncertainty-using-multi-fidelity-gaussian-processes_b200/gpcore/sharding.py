@@ -57,18 +57,34 @@ def trapezoids(n_pad, groups=8, block=128):
     return bands, frac
 
 
+_STAGING = {}
+
+
+def _staging(numel, like):
+    """One reusable contiguous staging tensor per (device, dtype), grown on demand: the bands of a factor broadcast go
+    through it one after the other, so a replication costs one allocation ever instead of one per band per call."""
+    key = (str(like.device), like.dtype)
+    buf = _STAGING.get(key)
+    if buf is None or buf.numel() < numel:
+        import torch
+        buf = _STAGING[key] = torch.empty(int(numel), dtype=like.dtype, device=like.device)
+    return buf
+
+
 def broadcast_lower(t2d, src=0, group=None, groups=8):
     """Broadcast the lower block-triangle of the square tensor ``t2d`` (any backend) band by band: the band is packed
-    into a contiguous buffer, broadcast, and written back on the receivers.  Returns the bytes broadcast."""
-    import torch
+    into a contiguous staging buffer, broadcast, and written back on the receivers.  Returns the bytes broadcast."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
     n = t2d.shape[0]
     bands, _ = trapezoids(n, groups)
+    stage = _staging(max((r1 - r0) * r1 for r0, r1 in bands), t2d)
     sent = 0
     for r0, r1 in bands:
         view = t2d[r0:r1, :r1]
-        buf = view.contiguous() if rank == src else torch.empty((r1 - r0, r1), dtype=t2d.dtype, device=t2d.device)
+        buf = stage[:(r1 - r0) * r1].view(r1 - r0, r1)
+        if rank == src:
+            buf.copy_(view)
         dist.broadcast(buf, src, group=group)
         if rank != src:
             view.copy_(buf)
